@@ -1,0 +1,142 @@
+/* include/lac_b200.h -- C ABI of liblac_b200.so, the B200 (sm_100a) implementation of
+ * the LAC block-parallel encode/decode hot path.
+ *
+ * This is the drop-in boundary: the reference's host code (WAV / .lac container I/O,
+ * block planning, CLI) keeps running on the CPU and calls these entry points where it
+ * used to run its std::thread worker pools over Block::Encoder / Block::Decoder:
+ *
+ *   lacb_encode*        replaces the worker-pool region of LAC::Encoder::encode
+ *                       (src/codec/lac/encoder.cpp:259-443: encode_block lambda,
+ *                       estimate_stereo_mode, Block::Encoder::encode) and returns what
+ *                       encoder.cpp:445-465 needs to write the block table + payload.
+ *   lacb_decode*        replaces LAC::Decoder's decode_block pool
+ *                       (src/codec/lac/decoder.cpp:167-292) and the CLI fast path's
+ *                       inner loop (src/main.cpp:317-407), including mid/side
+ *                       reconstruction, PCM range validation and WAV sample packing.
+ *   lacb_encode_block   Block::Encoder::encode (src/codec/block/encoder.cpp:313).
+ *   lacb_decode_block   Block::Decoder::decode_into (src/codec/block/decoder.cpp:64).
+ *   lacb_lpc_analyze    LPC::analyze_block_q15 (src/codec/lpc/lpc.cpp:156).
+ *
+ * Plain pointers and sizes only; no exceptions cross this boundary.  Every function
+ * returns 0 on success or a negative lacb_status; lacb_last_error() gives the text.
+ * There is no CPU fallback: without a CUDA device lacb_create fails.
+ */
+#ifndef LAC_B200_H
+#define LAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lacb_ctx lacb_ctx; /* one context = one GPU + one stream + its workspaces */
+
+typedef enum lacb_status {
+  LACB_OK = 0,
+  LACB_EINVAL = -1,  /* std::invalid_argument in the reference (lac/encoder.cpp:220-241) */
+  LACB_EDECODE = -2, /* "[decode-error] ..." (lac/decoder.cpp:25-32) */
+  LACB_ELIMIT = -3,  /* "encoded block size is outside format limits" (lac/encoder.cpp:447-450) */
+  LACB_ECUDA = -4,   /* CUDA runtime failure */
+  LACB_ENOMEM = -5
+} lacb_status;
+
+typedef enum lacb_layout {
+  LACB_PLANAR_I32 = 0,   /* two int32 planes (left, right); right ignored for mono        */
+  LACB_PACKED_LE = 1     /* interleaved little-endian 16/24-bit frames, as in a WAV chunk */
+} lacb_layout;
+
+typedef struct lacb_enc_params {
+  uint32_t sample_rate;          /* carried for the caller's frame header only            */
+  uint32_t bit_depth;            /* 16 or 24                                               */
+  uint32_t channels;             /* 1 or 2                                                 */
+  uint32_t stereo_mode;          /* 0 LR, 1 MS, 2 auto per block (--stereo-mode)           */
+  uint32_t zero_run_enabled;     /* LAC::Encoder::set_zero_run_enabled (default 1)         */
+  uint32_t partitioning_enabled; /* LAC::Encoder::set_partitioning_enabled (default 1)     */
+  uint32_t validate_range;       /* 1: reject samples outside bit_depth like the reference */
+} lacb_enc_params;
+
+typedef struct lacb_dec_params {
+  uint32_t bit_depth;   /* from the frame header */
+  uint32_t channels;
+  uint32_t stereo_mode;
+} lacb_dec_params;
+
+typedef struct lacb_err {
+  int32_t code;          /* lacb_status */
+  uint32_t block_index;  /* first failing block, when meaningful */
+  uint32_t reason;       /* decoder: 1 stereo flag, 2 primary, 3 secondary, 4 range, 5 trailing payload */
+  char msg[160];         /* reference-compatible message text */
+} lacb_err;
+
+/* Per-stage device times of the last call on this context (CUDA events on its stream). */
+typedef struct lacb_timing {
+  float h2d_ms, prep_ms, stereo_ms, lpc_ms, analyze_ms, finalize_ms, emit_ms, d2h_ms;
+  float parse_ms, finish_ms;
+  float total_ms;
+} lacb_timing;
+
+int lacb_create(int device, lacb_ctx** out);
+void lacb_destroy(lacb_ctx* ctx);
+const char* lacb_last_error(const lacb_ctx* ctx);
+void lacb_free(void* p);
+int lacb_device_count(void);
+int lacb_get_timing(const lacb_ctx* ctx, lacb_timing* out);
+
+/* Encode `frames` frames held in HOST memory.  The block plan is the reference's:
+ * fixed 16384-sample blocks, last one shorter (lac/encoder.cpp:59-69).
+ *   pcm_a / pcm_b : LACB_PLANAR_I32 -> left / right int32 planes (pcm_b NULL for mono)
+ *                   LACB_PACKED_LE  -> pcm_a = interleaved bytes, pcm_b unused
+ *   payload_out   : malloc'ed concatenation of all block payloads (lacb_free)
+ *   block_bytes   : caller array of ceil(frames/16384) entries, compressed bytes per block
+ */
+int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
+                uint64_t frames, uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes,
+                lacb_err* err);
+
+/* Same, with the int32 planes already resident on this context's device and the
+ * results left there.  *d_payload and *d_block_bytes point into the context's
+ * workspace and stay valid until the next call on the context. */
+int lacb_encode_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d_left, const int32_t* d_right,
+                       uint64_t frames, const uint8_t** d_payload, uint64_t* payload_bytes,
+                       const uint32_t** d_block_bytes, lacb_err* err);
+
+/* Decode n_blocks blocks whose concatenated payloads start at `payload` (HOST memory).
+ * block_sizes / block_bytes come from the v3 block table.  Output (HOST memory):
+ *   LACB_PLANAR_I32 -> out_a / out_b int32 planes (out_b NULL for mono)
+ *   LACB_PACKED_LE  -> out_a = interleaved little-endian bit_depth/8-byte samples
+ */
+int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payload, uint64_t payload_bytes,
+                const uint32_t* block_sizes, const uint32_t* block_bytes, uint32_t n_blocks, int layout,
+                void* out_a, void* out_b, lacb_err* err);
+
+/* Device-resident variant: payload and the two tables are device pointers, the planes
+ * are written to d_left / d_right (device), optional packed output to d_packed. */
+int lacb_decode_device(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* d_payload, uint64_t payload_bytes,
+                       const uint32_t* block_sizes_host, const uint32_t* block_bytes_host, uint32_t n_blocks,
+                       int32_t* d_left, int32_t* d_right, uint8_t* d_packed, lacb_err* err);
+
+/* Block-level hooks (what the reference's own unit tests exercise). */
+int lacb_encode_block(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int zero_run, int partitioning,
+                      uint8_t** out, uint64_t* out_size);
+/* returns 1 when accepted (bits_consumed set), 0 when rejected, <0 on failure */
+int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_t block_size, int32_t* out,
+                      uint64_t* bits_consumed);
+/* coeffs_out[0..order]; returns used_order (0 = unstable) or <0 */
+int lacb_lpc_analyze(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int order, int16_t* coeffs_out);
+
+/* Debug: decision record of the last lacb_encode_block call. */
+typedef struct lacb_block_info {
+  uint32_t predictor_type, order, partition_order, n_parts, taps;
+  int16_t coeffs[13];
+  uint8_t part_mode[256], part_k[256];
+  uint32_t cand_best_lo[11];
+  uint32_t bits;
+} lacb_block_info;
+int lacb_last_block_info(lacb_ctx* ctx, lacb_block_info* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAC_B200_H */

@@ -1,0 +1,643 @@
+// lacb_api.cu -- C ABI (include/lac_b200.h) over the sm_100a kernels.
+//
+// Host side of the device boundary: workspace management, stage launches on the
+// context's stream, and the two host<->device copies.  No codec arithmetic happens
+// on the host and there is no CPU fallback.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lac_b200.h"
+#include "lacb_dec_kernels.cuh"
+#include "lacb_enc_kernels.cuh"
+
+using namespace lacb;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+constexpr int FULL_NT = 1024, FULL_E = 16;  // 16384-sample channel-blocks: one CTA, 16 samples per thread
+constexpr int PROBE_NT = 32, PROBE_E = 8;   // 256-sample stereo probes: one warp
+constexpr size_t kFullSmem = ASmem<FULL_NT, FULL_E>::BYTES;
+constexpr size_t kProbeSmem = ASmem<PROBE_NT, PROBE_E>::BYTES;
+enum { EV_START = 0, EV_H2D, EV_PREP, EV_STEREO, EV_LPC, EV_ANALYZE, EV_FINAL, EV_EMIT, EV_D2H, EV_COUNT };
+}  // namespace
+
+struct lacb_ctx {
+  int device = 0;
+  int sms = 1;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  lacb_timing timing{};
+  cudaEvent_t ev[EV_COUNT] = {};
+  DevBuf packed_in, planeL, planeR, flags, jobs, jobs_p, counts, acor, acor_p, lpcq, lpcq_p, recs, probe_bytes,
+      blk_bytes, blk_off, misc, payload;
+  DevBuf d_payload, d_fs, d_size, d_boff, d_bytes, d_err, d_ms, d_L, d_R, d_packed;
+  void* pinned = nullptr;
+  size_t pinned_cap = 0;
+  lacb_block_info last_info{};
+};
+
+namespace {
+
+#define CK(call)                                                     \
+  do {                                                               \
+    cudaError_t _e = (call);                                         \
+    if (_e != cudaSuccess) {                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); \
+      return LACB_ECUDA;                                             \
+    }                                                                \
+  } while (0)
+#define CKR(expr)            \
+  do {                       \
+    const int _r = (expr);   \
+    if (_r != 0) return _r;  \
+  } while (0)
+
+int ensure(lacb_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  CK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+int ensure_pinned(lacb_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_cap) return 0;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_cap = 0;
+  CK(cudaMallocHost(&ctx->pinned, bytes + 256));
+  ctx->pinned_cap = bytes + 256;
+  return 0;
+}
+void set_err(lacb_err* e, int code, uint32_t block, uint32_t reason, const char* msg) {
+  if (!e) return;
+  e->code = code;
+  e->block_index = block;
+  e->reason = reason;
+  snprintf(e->msg, sizeof e->msg, "%s", msg);
+}
+float ev_ms(lacb_ctx* ctx, int a, int b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev[a], ctx->ev[b]);
+  return ms;
+}
+template <typename T>
+T* as(DevBuf& b) {
+  return reinterpret_cast<T*>(b.p);
+}
+uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// Device part of the encoder: planes already on the device.  On success the payload is
+// in ctx->payload, the per-block sizes in ctx->blk_bytes, *total the payload size.
+int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL, const int32_t* dR,
+                     uint64_t frames, bool validate, uint64_t* total, lacb_err* err) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t nb64 = (frames + kMaxBlock - 1) / kMaxBlock;
+  const uint32_t nb = (uint32_t)nb64;
+  EncCfg cfg;
+  cfg.channels = prm->channels;
+  cfg.stereo_mode = prm->channels == 2 ? prm->stereo_mode : 0u;  // lac/encoder.cpp:247
+  cfg.zero_run = prm->zero_run_enabled;
+  cfg.partitioning = prm->partitioning_enabled;
+  cfg.n_blocks = nb;
+  PcmSrc src{dL, prm->channels == 2 ? dR : nullptr, frames};
+  const bool automs = cfg.stereo_mode == 2u;
+
+  CKR(ensure(ctx, ctx->flags, (size_t)nb * 4));
+  CKR(ensure(ctx, ctx->jobs, (size_t)nb * 4 * 4));
+  CKR(ensure(ctx, ctx->counts, 64));
+  CKR(ensure(ctx, ctx->acor, (size_t)nb * 4 * 13 * 8));
+  CKR(ensure(ctx, ctx->lpcq, (size_t)nb * 4 * sizeof(LpcQ)));
+  CKR(ensure(ctx, ctx->recs, (size_t)nb * 4 * sizeof(ChanRec)));
+  CKR(ensure(ctx, ctx->blk_bytes, (size_t)nb * 4));
+  CKR(ensure(ctx, ctx->blk_off, (size_t)nb * 8));
+  CKR(ensure(ctx, ctx->misc, 64));
+  if (automs) {
+    CKR(ensure(ctx, ctx->jobs_p, (size_t)nb * 12 * 4));
+    CKR(ensure(ctx, ctx->acor_p, (size_t)nb * 12 * 13 * 8));
+    CKR(ensure(ctx, ctx->lpcq_p, (size_t)nb * 12 * sizeof(LpcQ)));
+    CKR(ensure(ctx, ctx->probe_bytes, (size_t)nb * 12 * 4));
+  }
+  uint32_t* counts = as<uint32_t>(ctx->counts);  // [0] full jobs, [1] probe jobs
+  uint32_t* miscw = as<uint32_t>(ctx->misc);     // [0] range error, [1] size error, [2..3] total bytes
+  CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
+  CK(cudaMemsetAsync(ctx->counts.p, 0, 64, st));
+
+  const uint32_t wide = umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 8u);
+  if (validate) {
+    auto kv = k_validate;
+    LACB_LAUNCH(kv, wide ? wide : 1u, 256, 0, st, src, prm->bit_depth, miscw);
+  }
+  CK(cudaEventRecord(ctx->ev[EV_PREP], st));
+
+  // stereo decision (mode 2): proxy, then 3x256-sample probes for the uncertain blocks
+  if (automs) {
+    auto kp = k_stereo_proxy;
+    LACB_LAUNCH(kp, umin(nb, (uint32_t)ctx->sms * 8u), 256, 0, st, src, cfg, as<uint32_t>(ctx->flags));
+    auto kb = k_build_jobs<true>;
+    LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs_p), counts + 1);
+    const uint32_t pgrid = umin(nb * 12u, (uint32_t)ctx->sms * 16u);
+    auto ka = k_autocorr<PROBE_NT, PROBE_E, true>;
+    LACB_LAUNCH(ka, pgrid, PROBE_NT, PROBE_NT * PROBE_E * 4, st, src, as<uint32_t>(ctx->jobs_p), counts + 1,
+                as<i64>(ctx->acor_p));
+    auto kl = k_levinson<true>;
+    LACB_LAUNCH(kl, umin((nb * 12u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs_p),
+                counts + 1, as<i64>(ctx->acor_p), as<LpcQ>(ctx->lpcq_p));
+    auto kz = k_analyze<PROBE_NT, PROBE_E, true>;
+    LACB_LAUNCH(kz, pgrid, PROBE_NT, kProbeSmem, st, src, cfg, as<uint32_t>(ctx->jobs_p),
+                counts + 1, as<LpcQ>(ctx->lpcq_p), (ChanRec*)nullptr, as<uint32_t>(ctx->probe_bytes));
+    auto kd = k_decide_probes;
+    LACB_LAUNCH(kd, umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags),
+                as<uint32_t>(ctx->probe_bytes));
+  } else {
+    auto kf = k_plan_fixed;
+    LACB_LAUNCH(kf, umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags));
+  }
+  CK(cudaEventRecord(ctx->ev[EV_STEREO], st));
+
+  // LPC analysis and the channel-block search on the selected channels
+  {
+    auto kb = k_build_jobs<false>;
+    LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs), counts);
+    const uint32_t fgrid = umin(nb * 4u, (uint32_t)ctx->sms);
+    auto ka = k_autocorr<FULL_NT, FULL_E, false>;
+    LACB_LAUNCH(ka, fgrid, FULL_NT, FULL_NT * FULL_E * 4, st, src, as<uint32_t>(ctx->jobs), counts,
+                as<i64>(ctx->acor));
+    auto kl = k_levinson<false>;
+    LACB_LAUNCH(kl, umin((nb * 4u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs),
+                counts, as<i64>(ctx->acor), as<LpcQ>(ctx->lpcq));
+    CK(cudaEventRecord(ctx->ev[EV_LPC], st));
+    auto kz = k_analyze<FULL_NT, FULL_E, false>;
+    LACB_LAUNCH(kz, fgrid, FULL_NT, kFullSmem, st, src, cfg, as<uint32_t>(ctx->jobs), counts,
+                as<LpcQ>(ctx->lpcq), as<ChanRec>(ctx->recs), (uint32_t*)nullptr);
+  }
+  CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));
+
+  // block sizes, final LR/MS pick of "encode both" blocks, payload offsets
+  {
+    auto kf = k_finalize_blocks;
+    LACB_LAUNCH(kf, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<ChanRec>(ctx->recs),
+                as<uint32_t>(ctx->blk_bytes), as<u64>(ctx->blk_off), reinterpret_cast<u64*>(miscw + 2), miscw + 1);
+  }
+  CK(cudaEventRecord(ctx->ev[EV_FINAL], st));
+  uint32_t hmisc[4];
+  CK(cudaMemcpyAsync(hmisc, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (hmisc[0]) {
+    ctx->err = "sample outside bit depth range";
+    set_err(err, LACB_EINVAL, 0, 0, "sample outside bit depth range");
+    return LACB_EINVAL;
+  }
+  if (hmisc[1]) {
+    ctx->err = "encoded block size is outside format limits";
+    set_err(err, LACB_ELIMIT, 0, 0, "encoded block size is outside format limits");
+    return LACB_ELIMIT;
+  }
+  uint64_t tot;
+  memcpy(&tot, hmisc + 2, 8);
+  *total = tot;
+  CKR(ensure(ctx, ctx->payload, (size_t)tot + 8));
+  {
+    auto ke = k_emit<FULL_NT, FULL_E>;
+    LACB_LAUNCH(ke, umin(nb * cfg.channels, (uint32_t)ctx->sms), FULL_NT, kFullSmem, st, src, cfg,
+                as<uint32_t>(ctx->flags), as<ChanRec>(ctx->recs), as<u64>(ctx->blk_off), as<uint8_t>(ctx->payload));
+  }
+  CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
+  return 0;
+}
+
+void fill_enc_timing(lacb_ctx* ctx) {
+  lacb_timing& t = ctx->timing;
+  memset(&t, 0, sizeof t);
+  t.h2d_ms = ev_ms(ctx, EV_START, EV_H2D);
+  t.prep_ms = ev_ms(ctx, EV_H2D, EV_PREP);
+  t.stereo_ms = ev_ms(ctx, EV_PREP, EV_STEREO);
+  t.lpc_ms = ev_ms(ctx, EV_STEREO, EV_LPC);
+  t.analyze_ms = ev_ms(ctx, EV_LPC, EV_ANALYZE);
+  t.finalize_ms = ev_ms(ctx, EV_ANALYZE, EV_FINAL);
+  t.emit_ms = ev_ms(ctx, EV_FINAL, EV_EMIT);
+  t.d2h_ms = ev_ms(ctx, EV_EMIT, EV_D2H);
+  t.total_ms = ev_ms(ctx, EV_START, EV_D2H);
+}
+
+bool params_ok(const lacb_enc_params* p) {
+  return p && (p->channels == 1 || p->channels == 2) && (p->bit_depth == 16 || p->bit_depth == 24) &&
+         p->stereo_mode <= 2;
+}
+
+__global__ void k_decode_one(const uint8_t* data, u64 size, uint32_t n, int32_t* out, u64* result) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  BitSrc s;
+  bs_init(s, data, data + size);
+  const bool ok = decode_channel_block(s, size * 8ull, n, out);
+  result[0] = ok ? 1ull : 0ull;
+  result[1] = ok ? s.consumed : 0ull;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lacb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int lacb_create(int device, lacb_ctx** out) {
+  if (!out) return LACB_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return LACB_ECUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return LACB_ECUDA;
+  lacb_ctx* ctx = new lacb_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return LACB_ECUDA;
+  }
+  ctx->sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 1;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return LACB_ECUDA;
+  }
+  for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
+  cudaFuncSetAttribute(k_analyze<FULL_NT, FULL_E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)ASmem<FULL_NT, FULL_E>::BYTES);
+  cudaFuncSetAttribute(k_emit<FULL_NT, FULL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)ASmem<FULL_NT, FULL_E>::BYTES);
+  cudaFuncSetAttribute(k_autocorr<FULL_NT, FULL_E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       FULL_NT * FULL_E * 4);
+  if (cudaGetLastError() != cudaSuccess) {
+    lacb_destroy(ctx);
+    return LACB_ECUDA;
+  }
+  *out = ctx;
+  return LACB_OK;
+}
+
+void lacb_destroy(lacb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  DevBuf* all[] = {&ctx->packed_in, &ctx->planeL, &ctx->planeR, &ctx->flags, &ctx->jobs, &ctx->jobs_p, &ctx->counts,
+                   &ctx->acor, &ctx->acor_p, &ctx->lpcq, &ctx->lpcq_p, &ctx->recs, &ctx->probe_bytes,
+                   &ctx->blk_bytes, &ctx->blk_off, &ctx->misc, &ctx->payload, &ctx->d_payload, &ctx->d_fs,
+                   &ctx->d_size, &ctx->d_boff, &ctx->d_bytes, &ctx->d_err, &ctx->d_ms, &ctx->d_L, &ctx->d_R,
+                   &ctx->d_packed};
+  for (DevBuf* b : all) release(*b);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < EV_COUNT; ++i)
+    if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* lacb_last_error(const lacb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void lacb_free(void* p) { free(p); }
+int lacb_get_timing(const lacb_ctx* ctx, lacb_timing* out) {
+  if (!ctx || !out) return LACB_EINVAL;
+  *out = ctx->timing;
+  return 0;
+}
+
+int lacb_encode_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d_left, const int32_t* d_right,
+                       uint64_t frames, const uint8_t** d_payload, uint64_t* payload_bytes,
+                       const uint32_t** d_block_bytes, lacb_err* err) {
+  if (!ctx) return LACB_EINVAL;
+  if (!params_ok(prm) || !d_left || frames == 0 || (prm->channels == 2 && !d_right) ||
+      (frames + kMaxBlock - 1) / kMaxBlock > 0xFFFFFFu) {
+    ctx->err = "invalid encode arguments";
+    set_err(err, LACB_EINVAL, 0, 0, "invalid encode arguments");
+    return LACB_EINVAL;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+  CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+  uint64_t total = 0;
+  CKR(encode_on_device(ctx, prm, d_left, d_right, frames, prm->validate_range != 0, &total, err));
+  CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  fill_enc_timing(ctx);
+  if (d_payload) *d_payload = as<uint8_t>(ctx->payload);
+  if (payload_bytes) *payload_bytes = total;
+  if (d_block_bytes) *d_block_bytes = as<uint32_t>(ctx->blk_bytes);
+  return 0;
+}
+
+int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
+                uint64_t frames, uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes,
+                lacb_err* err) {
+  if (!ctx) return LACB_EINVAL;
+  if (!params_ok(prm) || !pcm_a || frames == 0 || !payload_out || !payload_bytes ||
+      (layout == LACB_PLANAR_I32 && prm->channels == 2 && !pcm_b) ||
+      (layout != LACB_PLANAR_I32 && layout != LACB_PACKED_LE) || (frames + kMaxBlock - 1) / kMaxBlock > 0xFFFFFFu) {
+    ctx->err = "invalid encode arguments";
+    set_err(err, LACB_EINVAL, 0, 0, "invalid encode arguments");
+    return LACB_EINVAL;
+  }
+  *payload_out = nullptr;
+  *payload_bytes = 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
+  CKR(ensure(ctx, ctx->planeL, frames * 4));
+  if (prm->channels == 2) CKR(ensure(ctx, ctx->planeR, frames * 4));
+  CK(cudaEventRecord(ctx->ev[EV_START], st));
+  bool validate = prm->validate_range != 0;
+  if (layout == LACB_PLANAR_I32) {
+    CK(cudaMemcpyAsync(ctx->planeL.p, pcm_a, frames * 4, cudaMemcpyHostToDevice, st));
+    if (prm->channels == 2) CK(cudaMemcpyAsync(ctx->planeR.p, pcm_b, frames * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], st));
+  } else {
+    const uint32_t bps = prm->bit_depth / 8;
+    const size_t bytes = (size_t)frames * prm->channels * bps;
+    CKR(ensure(ctx, ctx->packed_in, bytes + 4));
+    CK(cudaMemcpyAsync(ctx->packed_in.p, pcm_a, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], st));
+    const uint32_t grid = umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 16u);
+    auto kd = k_deinterleave;
+    LACB_LAUNCH(kd, grid ? grid : 1u, 256, 0, st, as<uint8_t>(ctx->packed_in), (u64)frames, prm->channels, bps,
+                as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR));
+    validate = false;  // a packed sample cannot leave its own bit depth
+  }
+  uint64_t total = 0;
+  CKR(encode_on_device(ctx, prm, as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR), frames, validate, &total, err));
+  uint8_t* host = (uint8_t*)malloc(total ? total : 1);
+  if (!host) return LACB_ENOMEM;
+  CK(cudaMemcpyAsync(host, ctx->payload.p, total, cudaMemcpyDeviceToHost, st));
+  if (block_bytes) CK(cudaMemcpyAsync(block_bytes, ctx->blk_bytes.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev[EV_D2H], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  fill_enc_timing(ctx);
+  *payload_out = host;
+  *payload_bytes = total;
+  return 0;
+}
+
+int lacb_encode_block(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int zero_run, int partitioning, uint8_t** out,
+                      uint64_t* out_size) {
+  if (!ctx || !pcm || n == 0 || n > kMaxBlock || !out || !out_size) return LACB_EINVAL;
+  lacb_enc_params prm{};
+  prm.sample_rate = 44100;
+  prm.bit_depth = 24;
+  prm.channels = 1;
+  prm.stereo_mode = 0;
+  prm.zero_run_enabled = zero_run ? 1u : 0u;
+  prm.partitioning_enabled = partitioning ? 1u : 0u;
+  prm.validate_range = 0;  // Block::Encoder accepts any int32
+  uint32_t bb = 0;
+  const int rc = lacb_encode(ctx, &prm, LACB_PLANAR_I32, pcm, nullptr, n, out, out_size, &bb, nullptr);
+  if (rc != 0) return rc;
+  ChanRec rec;
+  CK(cudaMemcpy(&rec, ctx->recs.p, sizeof rec, cudaMemcpyDeviceToHost));
+  lacb_block_info& bi = ctx->last_info;
+  memset(&bi, 0, sizeof bi);
+  bi.predictor_type = rec.type;
+  bi.order = rec.order;
+  bi.partition_order = rec.p;
+  bi.n_parts = 1u << rec.p;
+  bi.taps = rec.taps;
+  bi.bits = rec.bits;
+  for (int i = 0; i < 13; ++i) bi.coeffs[i] = rec.coef[i];
+  for (uint32_t i = 0; i < bi.n_parts; ++i) {
+    bi.part_mode[i] = rec.part[i] >> 5;
+    bi.part_k[i] = rec.part[i] & 31u;
+  }
+  for (int i = 0; i < 11; ++i) bi.cand_best_lo[i] = rec.cand_lo[i];
+  return 0;
+}
+
+int lacb_last_block_info(lacb_ctx* ctx, lacb_block_info* info) {
+  if (!ctx || !info) return LACB_EINVAL;
+  *info = ctx->last_info;
+  return 0;
+}
+
+int lacb_lpc_analyze(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int order, int16_t* coeffs_out) {
+  if (!ctx || !pcm || n == 0 || n > kMaxBlock || !coeffs_out || order < 4 || order > 12 || (order & 1))
+    return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CKR(ensure(ctx, ctx->planeL, (size_t)n * 4));
+  CKR(ensure(ctx, ctx->jobs, 16));
+  CKR(ensure(ctx, ctx->counts, 64));
+  CKR(ensure(ctx, ctx->acor, 4 * 13 * 8));
+  CKR(ensure(ctx, ctx->lpcq, 4 * sizeof(LpcQ)));
+  CK(cudaMemcpyAsync(ctx->planeL.p, pcm, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  const uint32_t one[2] = {0u, 1u};  // job list {slot 0}, count 1
+  CK(cudaMemcpyAsync(ctx->jobs.p, &one[0], 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->counts.p, &one[1], 4, cudaMemcpyHostToDevice, st));
+  PcmSrc src{as<int32_t>(ctx->planeL), nullptr, n};
+  auto ka = k_autocorr<FULL_NT, FULL_E, false>;
+  LACB_LAUNCH(ka, 1, FULL_NT, FULL_NT * FULL_E * 4, st, src, as<uint32_t>(ctx->jobs), as<uint32_t>(ctx->counts),
+              as<i64>(ctx->acor));
+  auto kl = k_levinson<false>;
+  LACB_LAUNCH(kl, 1, 64, 0, st, src, as<uint32_t>(ctx->jobs), as<uint32_t>(ctx->counts), as<i64>(ctx->acor),
+              as<LpcQ>(ctx->lpcq));
+  LpcQ q;
+  CK(cudaMemcpyAsync(&q, ctx->lpcq.p, sizeof q, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  const int c = (order - 4) / 2;
+  const uint32_t max_valid = n > 1u ? (n - 1u < 32u ? n - 1u : 32u) : 0u;
+  for (int i = 0; i <= order; ++i) coeffs_out[i] = 0;
+  if ((uint32_t)order > max_valid) return 0;
+  for (int i = 1; i <= order; ++i) coeffs_out[i] = q.coef[c][i];
+  return q.used[c];
+}
+
+// ---------------------------------------------------------------------------
+static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* d_payload, uint64_t payload_bytes,
+                         const uint32_t* block_sizes, const uint32_t* block_bytes, uint32_t n_blocks, int32_t* dL,
+                         int32_t* dR, uint8_t* d_packed, lacb_err* err) {
+  cudaStream_t st = ctx->stream;
+  // tables: first sample and byte offset of every block (host prefix sums, O(n_blocks))
+  const size_t tb = (size_t)n_blocks * (8 + 4 + 8 + 4);
+  CKR(ensure_pinned(ctx, tb));
+  u64* h_fs = reinterpret_cast<u64*>(ctx->pinned);
+  u64* h_boff = h_fs + n_blocks;
+  uint32_t* h_size = reinterpret_cast<uint32_t*>(h_boff + n_blocks);
+  uint32_t* h_bytes = h_size + n_blocks;
+  u64 fs = 0, bo = 0;
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    h_fs[b] = fs;
+    h_boff[b] = bo;
+    h_size[b] = block_sizes[b];
+    h_bytes[b] = block_bytes[b];
+    fs += block_sizes[b];
+    bo += block_bytes[b];
+  }
+  if (bo > payload_bytes) {
+    ctx->err = "compressed block sizes exceed frame payload";
+    set_err(err, LACB_EDECODE, 0, 0, "[decode-error] compressed block sizes exceed frame payload");
+    return LACB_EDECODE;
+  }
+  CKR(ensure(ctx, ctx->d_fs, (size_t)n_blocks * 8));
+  CKR(ensure(ctx, ctx->d_boff, (size_t)n_blocks * 8));
+  CKR(ensure(ctx, ctx->d_size, (size_t)n_blocks * 4));
+  CKR(ensure(ctx, ctx->d_bytes, (size_t)n_blocks * 4));
+  CKR(ensure(ctx, ctx->d_err, (size_t)n_blocks * 4));
+  CKR(ensure(ctx, ctx->d_ms, (size_t)n_blocks));
+  CK(cudaMemcpyAsync(ctx->d_fs.p, h_fs, (size_t)n_blocks * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_boff.p, h_boff, (size_t)n_blocks * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_size.p, h_size, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_bytes.p, h_bytes, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->ev[EV_H2D], st));
+  DecCfg cfg{prm->channels, prm->stereo_mode, prm->bit_depth, n_blocks};
+  auto kp = k_decode_blocks;
+  LACB_LAUNCH(kp, (n_blocks + 127u) / 128u, 128, 0, st, cfg, d_payload, as<u64>(ctx->d_fs), as<uint32_t>(ctx->d_size),
+              as<u64>(ctx->d_boff), as<uint32_t>(ctx->d_bytes), dL, dR, as<uint32_t>(ctx->d_err),
+              as<uint8_t>(ctx->d_ms));
+  CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));
+  auto kf = k_finish_pcm;
+  LACB_LAUNCH(kf, umin(n_blocks, (uint32_t)ctx->sms * 8u), 256, 0, st, cfg, as<u64>(ctx->d_fs),
+              as<uint32_t>(ctx->d_size), dL, dR, as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms), d_packed);
+  CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
+  return 0;
+}
+
+static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err) {
+  std::vector<uint32_t> herr(n_blocks);
+  CK(cudaMemcpyAsync(herr.data(), ctx->d_err.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    if (herr[b] == DERR_OK) continue;
+    char msg[160];
+    switch (herr[b]) {
+      case DERR_FLAG: snprintf(msg, sizeof msg, "[decode-error] invalid per-block stereo flag"); break;
+      case DERR_PRIMARY: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=primary", b); break;
+      case DERR_SECONDARY: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=secondary", b); break;
+      case DERR_RANGE: snprintf(msg, sizeof msg, "[decode-error] decoded sample outside PCM bit depth"); break;
+      default: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=trailing-payload", b); break;
+    }
+    ctx->err = msg;
+    set_err(err, LACB_EDECODE, b, herr[b], msg);
+    return LACB_EDECODE;
+  }
+  return 0;
+}
+
+static void fill_dec_timing(lacb_ctx* ctx) {
+  lacb_timing& t = ctx->timing;
+  memset(&t, 0, sizeof t);
+  t.h2d_ms = ev_ms(ctx, EV_START, EV_H2D);
+  t.parse_ms = ev_ms(ctx, EV_H2D, EV_ANALYZE);
+  t.finish_ms = ev_ms(ctx, EV_ANALYZE, EV_EMIT);
+  t.d2h_ms = ev_ms(ctx, EV_EMIT, EV_D2H);
+  t.total_ms = ev_ms(ctx, EV_START, EV_D2H);
+}
+
+static bool dec_params_ok(const lacb_dec_params* p) {
+  return p && (p->channels == 1 || p->channels == 2) && (p->bit_depth == 16 || p->bit_depth == 24) &&
+         p->stereo_mode <= 2 && !(p->channels == 1 && p->stereo_mode != 0);
+}
+
+int lacb_decode_device(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* d_payload, uint64_t payload_bytes,
+                       const uint32_t* block_sizes_host, const uint32_t* block_bytes_host, uint32_t n_blocks,
+                       int32_t* d_left, int32_t* d_right, uint8_t* d_packed, lacb_err* err) {
+  if (!ctx) return LACB_EINVAL;
+  if (!dec_params_ok(prm) || !d_payload || !block_sizes_host || !block_bytes_host || n_blocks == 0 || !d_left ||
+      (prm->channels == 2 && !d_right)) {
+    ctx->err = "invalid decode arguments";
+    return LACB_EINVAL;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
+  CKR(decode_common(ctx, prm, d_payload, payload_bytes, block_sizes_host, block_bytes_host, n_blocks, d_left, d_right,
+                    d_packed, err));
+  CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
+  const int rc = decode_check_errors(ctx, n_blocks, err);
+  fill_dec_timing(ctx);
+  return rc;
+}
+
+int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payload, uint64_t payload_bytes,
+                const uint32_t* block_sizes, const uint32_t* block_bytes, uint32_t n_blocks, int layout, void* out_a,
+                void* out_b, lacb_err* err) {
+  if (!ctx) return LACB_EINVAL;
+  if (!dec_params_ok(prm) || !payload || !block_sizes || !block_bytes || n_blocks == 0 || !out_a ||
+      (layout == LACB_PLANAR_I32 && prm->channels == 2 && !out_b) ||
+      (layout != LACB_PLANAR_I32 && layout != LACB_PACKED_LE)) {
+    ctx->err = "invalid decode arguments";
+    return LACB_EINVAL;
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  u64 frames = 0;
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    if (block_sizes[b] == 0 || block_sizes[b] > kMaxBlock) {
+      ctx->err = "invalid block size";
+      set_err(err, LACB_EDECODE, b, 0, "[decode-error] invalid block size");
+      return LACB_EDECODE;
+    }
+    frames += block_sizes[b];
+  }
+  const uint32_t bps = prm->bit_depth / 8;
+  CKR(ensure(ctx, ctx->d_payload, payload_bytes + 16));
+  CKR(ensure(ctx, ctx->d_L, frames * 4));
+  if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, frames * 4));
+  if (layout == LACB_PACKED_LE) CKR(ensure(ctx, ctx->d_packed, frames * prm->channels * bps));
+  CK(cudaEventRecord(ctx->ev[EV_START], st));
+  CK(cudaMemcpyAsync(ctx->d_payload.p, payload, payload_bytes, cudaMemcpyHostToDevice, st));
+  CKR(decode_common(ctx, prm, as<uint8_t>(ctx->d_payload), payload_bytes, block_sizes, block_bytes, n_blocks,
+                    as<int32_t>(ctx->d_L), as<int32_t>(ctx->d_R),
+                    layout == LACB_PACKED_LE ? as<uint8_t>(ctx->d_packed) : nullptr, err));
+  const int rc = decode_check_errors(ctx, n_blocks, err);
+  if (rc != 0) return rc;
+  if (layout == LACB_PACKED_LE) {
+    CK(cudaMemcpyAsync(out_a, ctx->d_packed.p, frames * prm->channels * bps, cudaMemcpyDeviceToHost, st));
+  } else {
+    CK(cudaMemcpyAsync(out_a, ctx->d_L.p, frames * 4, cudaMemcpyDeviceToHost, st));
+    if (prm->channels == 2) CK(cudaMemcpyAsync(out_b, ctx->d_R.p, frames * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaEventRecord(ctx->ev[EV_D2H], st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  fill_dec_timing(ctx);
+  return 0;
+}
+
+int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_t block_size, int32_t* out,
+                      uint64_t* bits_consumed) {
+  if (!ctx || !out) return LACB_EINVAL;
+  if (bits_consumed) *bits_consumed = 0;
+  if (block_size == 0 || block_size > kMaxBlock) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CKR(ensure(ctx, ctx->d_payload, size + 16));
+  CKR(ensure(ctx, ctx->d_L, (size_t)block_size * 4));
+  CKR(ensure(ctx, ctx->misc, 64));
+  if (size) CK(cudaMemcpyAsync(ctx->d_payload.p, data, size, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->d_L.p, 0, (size_t)block_size * 4, st));
+  auto kd = k_decode_one;
+  LACB_LAUNCH(kd, 1, 32, 0, st, as<uint8_t>(ctx->d_payload), (u64)size, block_size, as<int32_t>(ctx->d_L),
+              as<u64>(ctx->misc));
+  u64 res[2] = {0, 0};
+  CK(cudaMemcpyAsync(res, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(out, ctx->d_L.p, (size_t)block_size * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  if (bits_consumed) *bits_consumed = res[1];
+  return res[0] ? 1 : 0;
+}
+
+}  // extern "C"

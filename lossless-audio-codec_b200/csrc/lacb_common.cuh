@@ -1,0 +1,289 @@
+// lacb_common.cuh -- shared device primitives of the B200 LAC block codec.
+//
+// Everything here is integer/bit work; nothing uses tensor cores (the path is
+// ALU/HBM bound).  Reference citations are relative to the upstream
+// tree (audexdev/Lossless-Audio-Codec v1.4.0).
+#pragma once
+#include <stdint.h>
+
+#ifdef LACB_EMU
+// CPU fiber emulator build (tests/emu): test infrastructure, never shipped.
+#define LACB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  LACB_EMU_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+#define LACB_DYN_SMEM(type, name) LACB_EMU_DYN_SMEM(type, name)
+#else
+#include <cuda_runtime.h>
+#define LACB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define LACB_DYN_SMEM(type, name)                                  \
+  extern __shared__ __align__(16) unsigned char name##_raw_[];     \
+  type* name = reinterpret_cast<type*>(name##_raw_)
+#endif
+
+namespace lacb {
+
+// src/codec/block/constants.hpp:6-15, block/encoder.cpp:41-59, rice/rice.hpp:12-13
+constexpr uint32_t kMaxBlock = 16384;
+constexpr uint32_t kMinPart = 32;
+constexpr uint32_t kMaxPartOrder = 8;
+constexpr uint32_t kZrMinRun = 4;
+constexpr uint32_t kZrRunK = 2;
+constexpr uint32_t kDriftWin = 256;
+constexpr uint32_t kMicroWin = 96;
+enum : uint32_t { MODE_RICE = 0, MODE_ZR = 1, MODE_BIN = 2, MODE_STATIC = 3 };
+enum : uint32_t { PRED_FIXED = 0, PRED_FIR = 1, PRED_LPC = 2 };
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+typedef unsigned long long u64;
+typedef long long i64;
+
+// zig-zag, block/encoder.cpp:61-65 and rice/rice.cpp:7-15
+__device__ __forceinline__ uint32_t zz32(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
+__device__ __forceinline__ int32_t unzz32(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
+
+__device__ __forceinline__ uint32_t bitwidth64(u64 v) { return 64u - (uint32_t)__clzll((i64)v); }
+
+// Conflict-free shared-memory layout for "thread t owns E consecutive words":
+// 16-byte chunks are XOR-swizzled inside groups of 64 chunks so that the LDS.128
+// a quarter-warp issues for chunk c of 8 consecutive threads hits 8 distinct bank
+// groups for E = 8, 16 or 32.
+__device__ __forceinline__ uint32_t swz_chunk(uint32_t q) { return q ^ ((q >> 3) & 7u); }
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return (swz_chunk(i >> 2) << 2) | (i & 3u); }
+
+// ---------------------------------------------------------------------------
+// Adaptive Rice parameter, division-free closed forms.
+//
+// Stateless model (block/encoder.cpp:72-77): mean = (sum + (count>>1)) / count,
+// k = mean <= 1 ? 0 : min(31, bit_width(mean-1)).  With N = sum + (count>>1):
+//   bit_width(floor(N/c) - 1) = min{ w >= 1 : N < ((1<<w) + 1) * c }.
+// `hint` is a guess for the answer (e.g. the previous sample's k): the search walks
+// from it, so a good hint costs two comparisons.
+__device__ __forceinline__ uint32_t kbase_from(u64 N, uint32_t c, uint32_t hint) {
+  if (N < 2ull * c) return 0u;  // mean <= 1
+  // smallest w in [1,32] with N < (c << w) + c ; N < 2^47, c < 2^15 so no overflow up to w = 48
+  uint32_t w = hint < 1u ? 1u : (hint > 33u ? 33u : hint);
+  while (w > 1u && N < (((u64)c) << (w - 1u)) + c) --w;   // (w-1) also satisfies -> go down
+  while (w < 33u && !(N < (((u64)c) << w) + c)) ++w;      // w does not satisfy -> go up
+  return w > 31u ? 31u : w;
+}
+__device__ __forceinline__ uint32_t kbase_guess(u64 N, uint32_t c) {
+  // floor(log2(N)) - floor(log2(c)) is within +-1 of the answer
+  const int g = (int)bitwidth64(N) - (int)(32 - __clz((int)c));
+  return g < 1 ? 1u : (uint32_t)g;
+}
+
+// rice_bits_for_unsigned, block/encoder.cpp:67-70
+__device__ __forceinline__ u64 rice_cost(uint32_t u, uint32_t k) {
+  const uint32_t q = (k >= 31u) ? 0u : (u >> k);
+  return (u64)q + 1u + k;
+}
+
+// ---------------------------------------------------------------------------
+// Block-wide primitives.  `scratch` holds 33 entries per scanned value; every call
+// ends with a barrier so the scratch can be reused immediately.
+template <int NT>
+__device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64* scratch, u64* total) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  constexpr int NW = (NT + 31) / 32;
+  u64 inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 y = __shfl_up_sync(kFull, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
+  }
+  if (NW == 1) {
+    if (total) *total = __shfl_sync(kFull, inc, 31);
+    return inc - v;
+  }
+  if (lane == 31u) scratch[w] = inc;
+  __syncthreads();
+  u64 ws = (lane < (uint32_t)NW) ? scratch[lane] : 0ull;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 y = __shfl_up_sync(kFull, ws, d);
+    if (lane >= (uint32_t)d) ws += y;
+  }
+  const u64 wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
+  const u64 tot = __shfl_sync(kFull, ws, NW - 1);
+  __syncthreads();
+  if (total) *total = tot;
+  return (w ? wprev : 0ull) + inc - v;
+}
+
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  constexpr int NW = (NT + 31) / 32;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(kFull, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
+  }
+  if (NW == 1) {
+    if (total) *total = __shfl_sync(kFull, inc, 31);
+    return inc - v;
+  }
+  if (lane == 31u) scratch[w] = inc;
+  __syncthreads();
+  uint32_t ws = (lane < (uint32_t)NW) ? scratch[lane] : 0u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(kFull, ws, d);
+    if (lane >= (uint32_t)d) ws += y;
+  }
+  const uint32_t wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
+  const uint32_t tot = __shfl_sync(kFull, ws, NW - 1);
+  __syncthreads();
+  if (total) *total = tot;
+  return (w ? wprev : 0u) + inc - v;
+}
+
+// exclusive running maximum of a signed value (identity = -1)
+template <int NT>
+__device__ __forceinline__ int32_t block_excl_max_i32(int32_t v, int32_t* scratch) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  constexpr int NW = (NT + 31) / 32;
+  int32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t y = __shfl_up_sync(kFull, inc, d);
+    if (lane >= (uint32_t)d && y > inc) inc = y;
+  }
+  int32_t ex = __shfl_up_sync(kFull, inc, 1);
+  if (lane == 0u) ex = -1;
+  if (NW == 1) return ex;
+  if (lane == 31u) scratch[w] = inc;
+  __syncthreads();
+  int32_t ws = (lane < (uint32_t)NW) ? scratch[lane] : -1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t y = __shfl_up_sync(kFull, ws, d);
+    if (lane >= (uint32_t)d && y > ws) ws = y;
+  }
+  const int32_t wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
+  __syncthreads();
+  if (w && wprev > ex) ex = wprev;
+  return ex;
+}
+
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// Bit-plane population counts.
+//
+// sum_i (u_i >> k) for every k follows from the per-bit-plane set counts c_b:
+//   T_0 = sum u,   T_{k+1} = (T_k - c_k) >> 1          (exact, any 32-bit u)
+// which turns estimate_static_k / estimate_initial_k (block/encoder.cpp:121-188,
+// ~57% of the CPU encoder's time) into a handful of logic ops per sample.
+// Counts are kept packed two planes per 32-bit word (16-bit fields; a block has at
+// most 16384 samples): word w = c_{2w} | c_{2w+1} << 16, planes 0..15.
+struct PlaneCounts {
+  uint32_t w[8];
+};
+
+// Vertical (bit-sliced) population count of E words with carry-save adders:
+// bit b of V[i] is bit i of the number of inputs that have bit b set.
+template <int E>
+__device__ __forceinline__ void csa_count(const uint32_t (&u)[E], uint32_t (&V)[5]) {
+  static_assert(E == 8 || E == 16, "E must be 8 or 16");
+#define LACB_FA(a, b, c, s, cy)            \
+  {                                        \
+    const uint32_t _a = (a), _b = (b), _c = (c); \
+    s = _a ^ _b ^ _c;                      \
+    cy = (_a & _b) | (_c & (_a ^ _b));     \
+  }
+  if constexpr (E == 16) {
+    uint32_t s0, s1, s2, s3, s4, s5, s6, c0, c1, c2, c3, c4, c5, c6;
+    LACB_FA(u[0], u[1], u[2], s0, c0);
+    LACB_FA(u[3], u[4], u[5], s1, c1);
+    LACB_FA(u[6], u[7], u[8], s2, c2);
+    LACB_FA(u[9], u[10], u[11], s3, c3);
+    LACB_FA(u[12], u[13], u[14], s4, c4);
+    LACB_FA(s0, s1, s2, s5, c5);
+    LACB_FA(s3, s4, u[15], s6, c6);
+    V[0] = s5 ^ s6;
+    const uint32_t c7 = s5 & s6;
+    uint32_t t0, t1, t2, d0, d1, d2;
+    LACB_FA(c0, c1, c2, t0, d0);
+    LACB_FA(c3, c4, c5, t1, d1);
+    LACB_FA(c6, c7, t0, t2, d2);
+    V[1] = t1 ^ t2;
+    const uint32_t d3 = t1 & t2;
+    uint32_t e0, f0;
+    LACB_FA(d0, d1, d2, e0, f0);
+    V[2] = e0 ^ d3;
+    const uint32_t f1 = e0 & d3;
+    V[3] = f0 ^ f1;
+    V[4] = f0 & f1;
+  } else {
+    uint32_t s0, s1, c0, c1, s2, c2;
+    LACB_FA(u[0], u[1], u[2], s0, c0);
+    LACB_FA(u[3], u[4], u[5], s1, c1);
+    LACB_FA(s0, s1, u[6], s2, c2);
+    V[0] = s2 ^ u[7];
+    const uint32_t c3 = s2 & u[7];
+    uint32_t t0, d0;
+    LACB_FA(c0, c1, c2, t0, d0);
+    V[1] = t0 ^ c3;
+    const uint32_t d1 = t0 & c3;
+    V[2] = d0 ^ d1;
+    V[3] = d0 & d1;
+    V[4] = 0u;
+  }
+#undef LACB_FA
+}
+
+// bit-sliced counters -> packed per-plane counts (planes 0..15)
+__device__ __forceinline__ void planes_from_sliced(const uint32_t (&V)[5], PlaneCounts& pc) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    uint32_t lo = 0u, hi = 0u;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      lo |= ((V[i] >> (2 * w)) & 1u) << i;
+      hi |= ((V[i] >> (2 * w + 1)) & 1u) << i;
+    }
+    pc.w[w] = lo | (hi << 16);
+  }
+}
+__device__ __forceinline__ uint32_t plane_get(const PlaneCounts& pc, int b) {
+  return (pc.w[b >> 1] >> ((b & 1) * 16)) & 0xFFFFu;
+}
+// adds the bit planes of one value
+__device__ __forceinline__ void planes_add_value(PlaneCounts& pc, uint32_t u) {
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    const uint32_t t = u >> (2 * w);
+    pc.w[w] += (t & 1u) + ((t & 2u) << 15);
+  }
+}
+
+// argmin_k (T_k + cnt*(1+k)) for k in [0,kmax], first minimum wins
+// (estimate_initial_k kmax=12, estimate_static_k kmax=15; block/encoder.cpp:121-180).
+__device__ __forceinline__ uint32_t best_static_k(u64 T0, const PlaneCounts& pc, uint32_t cnt, int kmax,
+                                                  u64* bits_out) {
+  u64 T = T0, best = ~0ull;
+  uint32_t bk = 0;
+  for (int k = 0; k <= kmax; ++k) {
+    const u64 cost = T + (u64)cnt * (uint32_t)(1 + k);
+    if (cost < best) {
+      best = cost;
+      bk = (uint32_t)k;
+    }
+    T = (T - plane_get(pc, k)) >> 1;
+  }
+  if (bits_out) *bits_out = best;
+  return bk;
+}
+
+}  // namespace lacb

@@ -1,0 +1,751 @@
+// lacb_enc_kernels.cuh -- encoder kernels (sm_100a): de-interleave, stereo proxy,
+// autocorrelation, Levinson, channel-block analysis, block-offset scan, emission.
+#pragma once
+#include "lacb_encode.cuh"
+#include "lacb_f80.cuh"
+
+namespace lacb {
+
+// Per-block flag word shared by the encoder stages.
+enum : uint32_t {
+  BF_CHOOSE_MS = 1u,     // mid/side selected (stereo)
+  BF_UNCERTAIN = 2u,     // estimate_stereo_mode said "uncertain"
+  BF_PROBE = 4u,         // uncertain and size > 4096: decided by 3x256-sample probes
+  BF_BOTH = 8u,          // uncertain and size <= 4096: both pairs encoded, smaller wins
+  BF_NEED_SHIFT = 4u,    // bits 4..7: channel kinds (L,R,M,S) that need a full analysis
+};
+
+struct EncCfg {
+  uint32_t channels;      // 1 or 2
+  uint32_t stereo_mode;   // effective: 0 LR, 1 MS, 2 auto (0 for mono)
+  uint32_t zero_run;      // set_zero_run_enabled
+  uint32_t partitioning;  // set_partitioning_enabled
+  uint32_t n_blocks;
+};
+
+__device__ __forceinline__ uint32_t block_len(u64 frames, uint32_t b) {
+  const u64 start = (u64)b * kMaxBlock;
+  const u64 left = frames - start;
+  return left < kMaxBlock ? (uint32_t)left : kMaxBlock;
+}
+
+struct JobDesc {
+  u64 start;
+  uint32_t n;
+  int kind;
+};
+// Full-analysis slots: 4 per block (L,R,M,S).  Probe slots: 12 per block
+// (3 positions x L,R,M,S; lac/encoder.cpp:343-353).
+template <bool PROBE>
+__device__ __forceinline__ void job_desc(const PcmSrc& src, uint32_t slot, JobDesc& jd) {
+  if (PROBE) {
+    const uint32_t b = slot / 12u, q = slot - b * 12u;
+    const uint32_t nb = block_len(src.frames, b);
+    const uint32_t t = q >> 2;
+    const uint32_t off = t == 0u ? 0u : (t == 1u ? (nb - 256u) / 2u : nb - 256u);
+    jd.start = (u64)b * kMaxBlock + off;
+    jd.n = 256u;
+    jd.kind = (int)(q & 3u);
+    return;
+  }
+  const uint32_t b = slot >> 2, s = slot & 3u;
+  jd.start = (u64)b * kMaxBlock;
+  jd.n = block_len(src.frames, b);
+  jd.kind = (int)s;
+}
+
+// Compacts the active analysis slots of every block into a job list (single CTA; the
+// per-GPU table has at most ~10^5 blocks).  Probe slots are active for BF_PROBE blocks,
+// full slots follow the need mask.
+template <bool PROBE>
+__global__ void __launch_bounds__(1024) k_build_jobs(EncCfg cfg, const uint32_t* blk_flags, uint32_t* jobs,
+                                                     uint32_t* job_count) {
+  __shared__ uint32_t scr[40];
+  __shared__ uint32_t carry;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0u) carry = 0u;
+  __syncthreads();
+  for (uint32_t base = 0; base < cfg.n_blocks; base += 1024u) {
+    const uint32_t b = base + tid;
+    uint32_t mask = 0u;
+    if (b < cfg.n_blocks) {
+      const uint32_t f = blk_flags[b];
+      mask = PROBE ? ((f & BF_PROBE) ? 0xFFFu : 0u) : ((f >> BF_NEED_SHIFT) & 0xFu);
+    }
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan_u32<1024>((uint32_t)__popc(mask), scr, &tot);
+    uint32_t o = carry + ex;
+    for (uint32_t s = 0; s < (PROBE ? 12u : 4u); ++s)
+      if ((mask >> s) & 1u) jobs[o++] = b * (PROBE ? 12u : 4u) + s;
+    __syncthreads();
+    if (tid == 0u) carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0u) *job_count = carry;
+}
+
+// ---------------------------------------------------------------------------
+// K1: packed little-endian interleaved PCM -> int32 planes.  Each thread converts 4
+// frames; the packed bytes are read as aligned 32-bit words.
+__global__ void k_deinterleave(const uint8_t* __restrict__ in, u64 frames, uint32_t channels, uint32_t bps,
+                               int32_t* __restrict__ L, int32_t* __restrict__ R) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const uint32_t fb = channels * bps;  // bytes per frame
+  for (u64 f = (u64)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += stride) {
+    const uint8_t* p = in + f * fb;
+    for (uint32_t c = 0; c < channels; ++c) {
+      int32_t v;
+      if (bps == 2u) v = (int16_t)((uint32_t)p[0] | ((uint32_t)p[1] << 8));
+      else v = ((int32_t)(((uint32_t)p[0] << 8) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 24))) >> 8;
+      (c ? R : L)[f] = v;
+      p += bps;
+    }
+  }
+}
+
+// depth-range validation of planar input (lac/encoder.cpp:85-93,232-241)
+__global__ void k_validate(PcmSrc src, uint32_t depth, uint32_t* bad) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const int32_t lo = depth == 16u ? -32768 : -8388608, hi = depth == 16u ? 32767 : 8388607;
+  uint32_t any = 0u;
+  for (u64 f = (u64)blockIdx.x * blockDim.x + threadIdx.x; f < src.frames; f += stride) {
+    const int32_t l = src.L[f];
+    any |= (l < lo) | (l > hi);
+    if (src.R) {
+      const int32_t r = src.R[f];
+      any |= (r < lo) | (r > hi);
+    }
+  }
+  if (__any_sync(kFull, (int)any) && (threadIdx.x & 31u) == 0u) atomicOr(bad, 1u);
+}
+
+// ---------------------------------------------------------------------------
+// K2: estimate_stereo_mode (lac/encoder.cpp:126-197).  One CTA per block; 12
+// saturating sums (raw / first difference / first sum for L, R, M, S).
+__device__ __forceinline__ u64 zz64(i64 v) { return v >= 0 ? ((u64)v << 1) : ((((u64)(-(v + 1))) << 1) | 1ull); }
+__device__ __forceinline__ u64 sat_add(u64 a, u64 b) { return (b > ~0ull - a) ? ~0ull : a + b; }
+__device__ __forceinline__ u64 proxy_bits(u64 sum, u64 count) {
+  if (count == 0ull) return 0ull;
+  const u64 mean = (sum + (count >> 1)) / count;
+  uint32_t k = 0u;
+  while (k < 31u && (1ull << k) < mean) ++k;
+  return sat_add(sum >> k, count * (u64)(k + 1u));
+}
+__global__ void __launch_bounds__(256) k_stereo_proxy(PcmSrc src, EncCfg cfg, uint32_t* blk_flags) {
+  __shared__ u64 acc[12];
+  const uint32_t tid = threadIdx.x;
+  for (uint32_t b = blockIdx.x; b < cfg.n_blocks; b += gridDim.x) {
+    const uint32_t n = block_len(src.frames, b);
+    const u64 start = (u64)b * kMaxBlock;
+    if (tid < 12u) acc[tid] = 0ull;
+    __syncthreads();
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = 0ull;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+      i64 v[4], pv[4];
+      const i64 l = src.L[start + i], r = src.R[start + i];
+      v[0] = l; v[1] = r; v[2] = (l + r) >> 1; v[3] = l - r;
+      if (i > 0u) {
+        const i64 pl = src.L[start + i - 1u], prr = src.R[start + i - 1u];
+        pv[0] = pl; pv[1] = prr; pv[2] = (pl + prr) >> 1; pv[3] = pl - prr;
+      } else {
+        pv[0] = pv[1] = pv[2] = pv[3] = 0;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // per-sample terms are < 2^35, so plain adds cannot wrap within a block
+        s[c] += zz64(v[c]);
+        s[4 + c] += (i == 0u) ? zz64(v[c]) : zz64(v[c] - pv[c]);
+        s[8 + c] += (i == 0u) ? zz64(v[c]) : zz64(v[c] + pv[c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const u64 t = warp_sum_u64(s[i]);
+      if ((tid & 31u) == 0u) atomicAdd(&acc[i], t);
+    }
+    __syncthreads();
+    if (tid == 0u) {
+      u64 bits[4];
+      bool nondiff = false;
+      for (int c = 0; c < 4; ++c) {
+        const u64 rb = proxy_bits(acc[c], n), db = proxy_bits(acc[4 + c], n), ab = proxy_bits(acc[8 + c], n);
+        const u64 m = rb < db ? rb : db;
+        bits[c] = m < ab ? m : ab;
+        if (rb < db || ab < db) nondiff = true;
+      }
+      const u64 lr = sat_add(bits[0], bits[1]), ms = sat_add(bits[2], bits[3]);
+      const u64 smaller = lr < ms ? lr : ms;
+      const u64 diff = lr >= ms ? lr - ms : ms - lr;
+      const bool choose_ms = ms < lr;
+      const bool uncertain = smaller == 0ull || diff == 0ull || nondiff || diff <= smaller / 100ull;
+      uint32_t f = (choose_ms ? BF_CHOOSE_MS : 0u);
+      if (uncertain) {
+        f |= BF_UNCERTAIN;
+        if (n > 4096u) f |= BF_PROBE;
+        else f |= BF_BOTH | (0xFu << BF_NEED_SHIFT);
+      } else {
+        f |= (choose_ms ? 0xCu : 0x3u) << BF_NEED_SHIFT;
+      }
+      blk_flags[b] = f;
+    }
+    __syncthreads();
+  }
+}
+
+// flags for mono / forced stereo modes
+__global__ void k_plan_fixed(EncCfg cfg, uint32_t* blk_flags) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < cfg.n_blocks; b += gridDim.x * blockDim.x) {
+    uint32_t f;
+    if (cfg.channels == 1u) f = 0x1u << BF_NEED_SHIFT;
+    else if (cfg.stereo_mode == 1u) f = BF_CHOOSE_MS | (0xCu << BF_NEED_SHIFT);
+    else f = 0x3u << BF_NEED_SHIFT;
+    blk_flags[b] = f;
+  }
+}
+
+// After the probes: sum of the six LR and six MS probe sizes decides (lac/encoder.cpp:343-353)
+__global__ void k_decide_probes(EncCfg cfg, uint32_t* blk_flags, const uint32_t* probe_bytes) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < cfg.n_blocks; b += gridDim.x * blockDim.x) {
+    uint32_t f = blk_flags[b];
+    if (!(f & BF_PROBE)) continue;
+    u64 lr = 0, ms = 0;
+    for (uint32_t t = 0; t < 3u; ++t) {
+      lr += (u64)probe_bytes[b * 12u + t * 4u + 0u] + probe_bytes[b * 12u + t * 4u + 1u];
+      ms += (u64)probe_bytes[b * 12u + t * 4u + 2u] + probe_bytes[b * 12u + t * 4u + 3u];
+    }
+    const bool choose_ms = ms < lr;
+    f &= ~(BF_CHOOSE_MS | (0xFu << BF_NEED_SHIFT));
+    f |= choose_ms ? (BF_CHOOSE_MS | (0xCu << BF_NEED_SHIFT)) : (0x3u << BF_NEED_SHIFT);
+    blk_flags[b] = f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: exact int64 autocorrelation, lags 0..12 (lpc.cpp:80-96), one CTA per job.
+template <int NT, int E, bool PROBE>
+__global__ void __launch_bounds__(NT) k_autocorr(PcmSrc src, const uint32_t* jobs, const uint32_t* job_count, i64* acor) {
+  LACB_DYN_SMEM(unsigned char, smraw);
+  __shared__ u64 red[13];
+  int32_t* X = reinterpret_cast<int32_t*>(smraw);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nj = *job_count;
+  for (uint32_t ji = blockIdx.x; ji < nj; ji += gridDim.x) {
+    const uint32_t slot = jobs[ji];
+    JobDesc jd;
+    job_desc<PROBE>(src, slot, jd);
+    for (uint32_t i = tid; i < (uint32_t)(NT * E); i += NT) X[swz(i)] = i < jd.n ? load_sample(src, jd.kind, jd.start + i) : 0;
+    if (tid < 13u) red[tid] = 0ull;
+    __syncthreads();
+    int32_t x[E + 12];
+    {
+      const int4* X4 = reinterpret_cast<const int4*>(X);
+      const int q0 = (int)tid * (E / 4);
+#pragma unroll
+      for (int c = -3; c < E / 4; ++c) {
+        int4 v = make_int4(0, 0, 0, 0);
+        if (q0 + c >= 0) v = X4[swz_chunk((uint32_t)(q0 + c))];
+        x[12 + 4 * c + 0] = v.x; x[12 + 4 * c + 1] = v.y; x[12 + 4 * c + 2] = v.z; x[12 + 4 * c + 3] = v.w;
+      }
+    }
+    u64 s[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) s[k] = 0ull;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      // samples past n and before 0 are zero in X, so every term outside the sums vanishes
+#pragma unroll
+      for (int k = 0; k < 13; ++k) s[k] += (u64)((i64)x[12 + j] * (i64)x[12 + j - k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+      const u64 t = warp_sum_u64(s[k]);
+      if ((tid & 31u) == 0u) atomicAdd(&red[k], t);
+    }
+    __syncthreads();
+    if (tid < 13u) acor[(size_t)slot * 13u + tid] = (i64)red[tid];
+    __syncthreads();
+  }
+}
+
+// K6: Levinson-Durbin + Q15 quantisation, one thread per job (lpc.cpp:98-186).
+template <bool PROBE>
+__global__ void k_levinson(PcmSrc src, const uint32_t* jobs, const uint32_t* job_count, const i64* acor, LpcQ* lpcq) {
+  const uint32_t nj = *job_count;
+  for (uint32_t ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nj; ji += gridDim.x * blockDim.x) {
+    const uint32_t slot = jobs[ji];
+    JobDesc jd;
+    job_desc<PROBE>(src, slot, jd);
+    const uint32_t max_valid = jd.n > 1u ? (jd.n - 1u < 32u ? jd.n - 1u : 32u) : 0u;
+    int max_order = 0;
+    for (int co = 4; co <= 12; co += 2)
+      if ((uint32_t)co <= max_valid) max_order = co;
+    LpcQ out;
+    for (int c = 0; c < 5; ++c) out.pad[c] = 0;
+    if (max_order == 0) {
+      for (int c = 0; c < 5; ++c) {
+        out.used[c] = 0;
+        for (int i = 0; i < 13; ++i) out.coef[c][i] = 0;
+      }
+    } else {
+      i64 R[13];
+      for (int i = 0; i < 13; ++i) R[i] = acor[(size_t)slot * 13u + i];
+      levinson_q15(R, max_order, out.coef, out.used);
+    }
+    lpcq[slot] = out;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4+K7+K8+K9: channel-block analysis.
+struct BestCand {
+  u64 rice, zr, bin, stat, best;
+  uint32_t type, order, taps, ci, k_init, k_stat, has_run;
+  bool have;
+};
+
+template <int NT, int E>
+__device__ __forceinline__ u64 block_sum_u64(const ASmem<NT, E>& sm, u64 v) {
+  AMisc* mi = sm.Misc();
+  if (threadIdx.x == 0) mi->red64 = 0ull;
+  __syncthreads();
+  const u64 t = warp_sum_u64(v);
+  if ((threadIdx.x & 31u) == 0u && t) atomicAdd(&mi->red64, t);
+  __syncthreads();
+  const u64 r = mi->red64;
+  __syncthreads();
+  return r;
+}
+
+template <int NT, int E>
+__device__ __forceinline__ bool compute_residual(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n, uint32_t type,
+                                                 uint32_t order, uint32_t taps, const int16_t* coef, int32_t (&r)[E]) {
+  if (type == PRED_FIXED) {
+    residual_fixed<E>(x, g0, n, (int)order, r);
+    return false;
+  }
+  if (type == PRED_FIR) {
+    residual_fir<E>(x, g0, n, r);
+    return false;
+  }
+  return residual_lpc<E>(x, g0, n, coef, (int)taps, r);
+}
+
+template <int NT, int E, bool PROBE>
+__global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
+                                                const LpcQ* lpcq, ChanRec* recs, uint32_t* probe_bytes) {
+  LACB_DYN_SMEM(unsigned char, smraw);
+  ASmem<NT, E> sm{smraw};
+  AMisc* mi = sm.Misc();
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t nj = *job_count;
+  for (uint32_t ji = blockIdx.x; ji < nj; ji += gridDim.x) {
+    const uint32_t slot = jobs[ji];
+    JobDesc jd;
+    job_desc<PROBE>(src, slot, jd);
+    const uint32_t n = jd.n;
+    load_block<NT, E>(sm, src, jd.kind, jd.start, n);
+    __syncthreads();
+    int32_t x[E + 12];
+    load_items<NT, E>(sm, x);
+    const uint32_t max_valid = n > 1u ? (n - 1u < 32u ? n - 1u : 32u) : 0u;
+    const LpcQ* lq = lpcq + slot;
+
+    BestCand best;
+    best.have = false;
+    best.rice = best.zr = best.bin = best.stat = best.best = 0ull;
+    best.type = best.order = best.taps = best.ci = best.k_init = best.k_stat = best.has_run = 0u;
+    uint32_t cand_lo[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) cand_lo[i] = 0xFFFFFFFFu;
+
+    // candidate order: fixed 0..4, FIR, LPC 4,6,8,10,12 (block/encoder.cpp:362-407)
+    for (uint32_t ci = 0; ci < 11u; ++ci) {
+      int32_t r[E];
+      uint32_t type, order, taps = 0u;
+      if (ci <= 4u) {
+        type = PRED_FIXED;
+        order = ci;
+        residual_fixed<E>(x, g0, n, (int)ci, r);
+      } else if (ci == 5u) {
+        type = PRED_FIR;
+        order = 2u;
+        residual_fir<E>(x, g0, n, r);
+      } else {
+        const uint32_t c = ci - 6u, co = 4u + 2u * c;
+        if (co > max_valid) continue;
+        const uint32_t used = (uint32_t)lq->used[c];
+        if (used == 0u) continue;  // block/encoder.cpp:394-396
+        type = PRED_LPC;
+        order = co;
+        // compute_residual_q15 attempts (lpc.cpp:188-229): used, then {12,10,8,6,4} below it
+        uint32_t attempt = used < co ? used : co;
+        while (attempt > 0u) {
+          const bool ovf = residual_lpc<E>(x, g0, n, lq->coef[c], (int)attempt, r);
+          if (!__syncthreads_or((int)ovf)) {
+            taps = attempt;
+            break;
+          }
+          uint32_t next = 0u;
+          for (uint32_t fo = 12u; fo >= 4u; fo -= 2u)
+            if (fo < attempt && fo <= co) {
+              next = fo;
+              break;
+            }
+          attempt = next;
+        }
+        if (taps == 0u) continue;  // block/encoder.cpp:402-404
+      }
+      Prep<NT, E> pr;
+      prepare<NT, E, false>(sm, r, n, pr);
+      if (tid == 0u) {
+        PlaneCounts pf, pt;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          pf.w[w] = mi->cnt_first[w];
+          pt.w[w] = mi->cnt_tot[w];
+        }
+        const uint32_t cnt = n < 256u ? n : 256u;
+        mi->k_init = best_static_k(mi->p_first, pf, cnt, 12, nullptr);
+        u64 sb;
+        mi->k_stat = best_static_k(mi->u_total, pt, n, 15, &sb);
+        mi->stat_bits = sb;
+      }
+      __syncthreads();
+      cost_pass<NT, E, true>(sm, pr, n, 0u, mi->k_init);
+      const u64 rice = mi->tot_rice, bin = mi->tot_bin, stat = mi->stat_bits;
+      const uint32_t has_run = mi->has_run;
+      const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
+      const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
+      const u64 bb = m1 < m2 ? m1 : m2;
+      cand_lo[ci] = (uint32_t)bb;
+      if (!best.have || bb < best.best || (bb == best.best && type < best.type)) {  // :352-359
+        best.have = true;
+        best.rice = rice; best.zr = zr; best.bin = bin; best.stat = stat; best.best = bb;
+        best.type = type; best.order = order; best.taps = taps; best.ci = ci;
+        best.k_init = mi->k_init; best.k_stat = mi->k_stat; best.has_run = has_run;
+      }
+      __syncthreads();
+    }
+
+    // winner residual again, with the full prefix structures for the partition search
+    const int16_t* wcoef = best.type == PRED_LPC ? lq->coef[best.ci - 6u] : nullptr;
+    int32_t r[E];
+    compute_residual<NT, E>(x, g0, n, best.type, best.order, best.taps, wcoef, r);
+    Prep<NT, E> pr;
+    prepare<NT, E, true>(sm, r, n, pr);
+
+    const uint32_t max_p = (cfg.partitioning && n >= kMinPart) ? max_partition_order(n) : 0u;
+    // per-segment initial k, static k / bits and prefix of u, all levels at once
+    for (uint32_t sid = tid; sid < (2u << max_p) - 1u; sid += NT) {
+      const uint32_t p = 31u - (uint32_t)__clz((int)(sid + 1u));
+      const uint32_t s = sid + 1u - (1u << p);
+      const uint32_t base = n >> p, cnt = 1u << p;
+      const uint32_t a = s * base, b = (s + 1u == cnt) ? n : a + base;
+      const uint32_t len = b - a, f = a + (len < 256u ? len : 256u);
+      PlaneCounts ca, cf, cb;
+      prefix_counts<NT, E>(sm, a, ca);
+      prefix_counts<NT, E>(sm, f, cf);
+      prefix_counts<NT, E>(sm, b, cb);
+      const u64 pa = prefix_u<NT, E>(sm, a), pf = prefix_u<NT, E>(sm, f), pb = prefix_u<NT, E>(sm, b);
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        cf.w[w] -= ca.w[w];
+        cb.w[w] -= ca.w[w];
+      }
+      u64 sb;
+      const uint32_t ki = best_static_k(pf - pa, cf, f - a, 12, nullptr);
+      const uint32_t ks = best_static_k(pb - pa, cb, len, 15, &sb);
+      sm.SegP()[sid] = pa;
+      sm.SegStat()[sid] = sb;
+      sm.SegK()[sid] = (uint16_t)(ki | (ks << 8));
+    }
+    __syncthreads();
+
+    // base (p = 0) mode, block/encoder.cpp:432-484
+    const bool allow_zr = cfg.zero_run && best.has_run;
+    uint32_t base_mode = MODE_RICE, base_k = best.k_init;
+    u64 base_bits = best.rice;
+    if (allow_zr && best.zr <= base_bits) { base_bits = best.zr; base_mode = MODE_ZR; }
+    if (best.bin < base_bits) { base_bits = best.bin; base_mode = MODE_BIN; }
+    if (best.stat < base_bits) { base_bits = best.stat; base_mode = MODE_STATIC; base_k = best.k_stat; }
+    u64 best_total = base_bits + 15ull;
+    best_total += (8ull - (best_total & 7ull)) & 7ull;
+    uint32_t best_p = 0u;
+    if (tid == 0u) sm.SelMK()[0] = (uint8_t)((base_mode << 5) | base_k);
+    __syncthreads();
+
+    // partition search, block/encoder.cpp:486-545
+    for (uint32_t p = 1u; p <= max_p; ++p) {
+      cost_pass<NT, E, false>(sm, pr, n, p, 0u);
+      const uint32_t cnt = 1u << p;
+      const u64* Fb = sm.Fb();
+      u64 part_sum = 0ull;
+      for (uint32_t s = tid; s < cnt; s += NT) {
+        const uint32_t sid = cnt - 1u + s;
+        const u64 rice = Fb[s + 1u] - Fb[s], zr = Fb[258 + s + 1u] - Fb[258 + s], bin = Fb[516 + s + 1u] - Fb[516 + s];
+        const bool hr = (mi->hasrun_bits[s >> 5] >> (s & 31u)) & 1u;
+        const uint32_t kk = sm.SegK()[sid];
+        const u64 sbits = sm.SegStat()[sid];
+        uint32_t mode = MODE_RICE, k = kk & 0xFFu;
+        u64 bits = rice;
+        if (cfg.zero_run && hr && zr < bits) { mode = MODE_ZR; bits = zr; }
+        if (bin < bits) { mode = MODE_BIN; bits = bin; }
+        if (sbits < bits || sbits <= bits + bits / 20ull) { mode = MODE_STATIC; k = kk >> 8; bits = sbits; }  // :518, :190-192
+        sm.SelMK()[sid] = (uint8_t)((mode << 5) | k);
+        part_sum += bits;
+      }
+      const u64 sum_bits = block_sum_u64<NT, E>(sm, part_sum);
+      u64 total = sum_bits + 8ull + 7ull * cnt;
+      total += (8ull - (total & 7ull)) & 7ull;
+      const u64 margin = best_total / 20ull;
+      if (total < best_total || (total <= best_total + margin && best_p == 0u) ||
+          (total == best_total && p < best_p)) {  // :538-540
+        best_total = total;
+        best_p = p;
+      }
+    }
+
+    // exact emitted size of the chosen configuration (same token function as the emitter)
+    const uint32_t chosen_order =
+        best.type == PRED_LPC ? (best.taps < max_valid ? (best.taps > 1u ? best.taps : 1u) : (max_valid > 1u ? max_valid : 1u))
+                              : best.order;  // block/encoder.cpp:421-423
+    const uint32_t nparts = 1u << best_p;
+    u64 tok_bits = 0ull;
+    {
+      const SegGeom sg = seg_geom(g0, n, best_p);
+      uint8_t kn[E];
+      const uint8_t* mk = sm.SelMK();
+      const uint32_t mkA = mk[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? mk[sg.sidA + 1u] : 0u;
+      if (best_p == 0u) k_series<NT, E, true>(sm, pr, n, sg, kn);
+      else k_series<NT, E, false>(sm, pr, n, sg, kn);
+      walk_items<NT, E>(sm, pr, n, sg, kn, mkA & 31u, mkB & 31u,
+                        [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
+                            bool long_run) {
+                          const uint32_t m = inB ? mkB : mkA;
+                          bool emit;
+                          const Token t = make_token(m >> 5, m & 31u, u, k, is_zero, closes, long_run, &emit);
+                          if (emit) tok_bits += (u64)t.hlen + t.q + t.tlen;
+                        });
+    }
+    const u64 all_tok = block_sum_u64<NT, E>(sm, tok_bits);
+    const u64 bits = 16ull + (best.type == PRED_LPC ? 16ull * chosen_order : 0ull) + 8ull + 7ull * nparts + all_tok;
+    const u64 bytes = (bits + 7ull) >> 3;
+
+    if (PROBE) {
+      if (tid == 0u) probe_bytes[slot] = bytes > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bytes;
+    } else {
+      ChanRec* rec = recs + slot;
+      for (uint32_t s = tid; s < 256u; s += NT) rec->part[s] = s < nparts ? sm.SelMK()[nparts - 1u + s] : 0;
+      if (tid == 0u) {
+        rec->bytes = bytes > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bytes;
+        rec->bits = bits > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)bits;
+        rec->type = (uint8_t)best.type;
+        rec->order = (uint8_t)chosen_order;
+        rec->p = (uint8_t)best_p;
+        rec->taps = (uint8_t)best.taps;
+        for (int i = 0; i < 13; ++i) rec->coef[i] = (wcoef && i >= 1 && (uint32_t)i <= chosen_order) ? wcoef[i] : (int16_t)0;
+        rec->pad = 0;
+        for (int i = 0; i < 11; ++i) rec->cand_lo[i] = cand_lo[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-block sizes and the final LR/MS pick for "encode both" blocks, then an exclusive
+// scan of the block sizes (K11's device-wide prefix sum).  Single CTA: the table has at
+// most ~10^5 entries per GPU.
+__global__ void __launch_bounds__(1024) k_finalize_blocks(EncCfg cfg, uint32_t* blk_flags, const ChanRec* recs,
+                                                          uint32_t* blk_bytes, u64* blk_off, u64* total_bytes,
+                                                          uint32_t* err) {
+  __shared__ u64 scr[40];
+  __shared__ u64 carry;
+  const uint32_t tid = threadIdx.x;
+  if (tid == 0u) carry = 0ull;
+  __syncthreads();
+  for (uint32_t base = 0; base < cfg.n_blocks; base += 1024u) {
+    const uint32_t b = base + tid;
+    u64 sz = 0ull;
+    if (b < cfg.n_blocks) {
+      uint32_t f = blk_flags[b];
+      const ChanRec* rc = recs + (size_t)b * 4u;
+      if (cfg.channels == 1u) {
+        sz = rc[0].bytes;
+      } else {
+        if (f & BF_BOTH) {  // lac/encoder.cpp:336-340: MS only if strictly smaller
+          const u64 lr = (u64)rc[0].bytes + rc[1].bytes, ms = (u64)rc[2].bytes + rc[3].bytes;
+          f = (f & ~BF_CHOOSE_MS) | (ms < lr ? BF_CHOOSE_MS : 0u);
+          blk_flags[b] = f;
+        }
+        const uint32_t s0 = (f & BF_CHOOSE_MS) ? 2u : 0u;
+        sz = (u64)rc[s0].bytes + rc[s0 + 1u].bytes + (cfg.stereo_mode == 2u ? 1ull : 0ull);
+        if (rc[s0].bytes == 0xFFFFFFFFu || rc[s0 + 1u].bytes == 0xFFFFFFFFu) sz = 0x100000000ull;
+      }
+      if (sz == 0ull || sz > 0xFFFFFFFFull) {  // lac/encoder.cpp:447-450
+        atomicOr(err, 1u);
+        sz = 0ull;
+      }
+      blk_bytes[b] = (uint32_t)sz;
+    }
+    u64 tot;
+    const u64 ex = block_excl_scan_u64<1024>(sz, scr, &tot);
+    if (b < cfg.n_blocks) blk_off[b] = carry + ex;
+    __syncthreads();
+    if (tid == 0u) carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0u) *total_bytes = carry;
+}
+
+// ---------------------------------------------------------------------------
+// K10: emission.  One CTA per (block, channel); tokens are positioned by a block-wide
+// exclusive scan of their bit lengths and OR-ed into a shared-memory window that is
+// word-aligned with the destination, then stored with coalesced 32-bit writes.
+__device__ __forceinline__ void or_field(uint32_t* stg, uint32_t W, i64 rel, uint32_t value, uint32_t len) {
+  if (len == 0u) return;
+  if (rel + (i64)len <= 0 || rel >= (i64)W * 32) return;
+  const i64 widx = rel >> 5;  // arithmetic shift = floor
+  const uint32_t off = (uint32_t)(rel - widx * 32);
+  const u64 v = (u64)value << (64u - len - off);
+  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  if (widx >= 0 && widx < (i64)W && hi) atomicOr(&stg[widx], hi);
+  if (widx + 1 >= 0 && widx + 1 < (i64)W && lo) atomicOr(&stg[widx + 1], lo);
+}
+__device__ __forceinline__ void or_ones(uint32_t* stg, uint32_t W, i64 rel, uint32_t q) {
+  if (q == 0u) return;
+  i64 end = rel + (i64)q;  // exclusive
+  if (end <= 0 || rel >= (i64)W * 32) return;
+  if (rel < 0) rel = 0;
+  if (end > (i64)W * 32) end = (i64)W * 32;
+  uint32_t w0 = (uint32_t)(rel >> 5), w1 = (uint32_t)((end - 1) >> 5);
+  const uint32_t m0 = 0xFFFFFFFFu >> (uint32_t)(rel & 31), m1 = 0xFFFFFFFFu << (31u - (uint32_t)((end - 1) & 31));
+  if (w0 == w1) {
+    atomicOr(&stg[w0], m0 & m1);
+    return;
+  }
+  atomicOr(&stg[w0], m0);
+  for (uint32_t w = w0 + 1u; w < w1; ++w) atomicOr(&stg[w], 0xFFFFFFFFu);
+  atomicOr(&stg[w1], m1);
+}
+
+template <int NT, int E>
+__global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint32_t* blk_flags, const ChanRec* recs,
+                                             const u64* blk_off, uint8_t* payload) {
+  LACB_DYN_SMEM(unsigned char, smraw);
+  ASmem<NT, E> sm{smraw};
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t njobs = cfg.n_blocks * cfg.channels;
+  for (uint32_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+    const uint32_t b = job / cfg.channels, ch = job - b * cfg.channels;
+    const uint32_t f = blk_flags[b];
+    const uint32_t s0 = (cfg.channels == 2u && (f & BF_CHOOSE_MS)) ? 2u : 0u;
+    const ChanRec* rec = recs + (size_t)b * 4u + s0 + ch;
+    const uint32_t n = block_len(src.frames, b);
+    const bool flagged = cfg.channels == 2u && cfg.stereo_mode == 2u;
+    u64 out_off = blk_off[b] + (flagged ? 1ull : 0ull);
+    if (ch == 1u) out_off += recs[(size_t)b * 4u + s0].bytes;
+    if (flagged && ch == 0u && tid == 0u) payload[blk_off[b]] = (f & BF_CHOOSE_MS) ? 1 : 0;
+
+    load_block<NT, E>(sm, src, (int)(s0 + ch), (u64)b * kMaxBlock, n);
+    __syncthreads();
+    int32_t x[E + 12];
+    load_items<NT, E>(sm, x);
+    const uint32_t type = rec->type, order = rec->order, p = rec->p, nparts = 1u << p;
+    int32_t r[E];
+    compute_residual<NT, E>(x, g0, n, type, order, rec->taps, rec->coef, r);
+    Prep<NT, E> pr;
+    prepare<NT, E, false>(sm, r, n, pr);  // U plane, prefix of u, last-nonzero scan (plane totals unused)
+    // segment tables of the chosen level
+    for (uint32_t s = tid; s < nparts; s += NT) {
+      const uint32_t sid = nparts - 1u + s;
+      sm.SelMK()[sid] = rec->part[s];
+      sm.SegP()[sid] = p ? prefix_u<NT, E>(sm, s * (n >> p)) : 0ull;
+    }
+    __syncthreads();
+    const SegGeom sg = seg_geom(g0, n, p);
+    uint8_t kn[E];
+    const uint32_t mkA = sm.SelMK()[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? sm.SelMK()[sg.sidA + 1u] : 0u;
+    if (p == 0u) k_series<NT, E, true>(sm, pr, n, sg, kn);
+    else k_series<NT, E, false>(sm, pr, n, sg, kn);
+    u64 my_bits = 0ull;
+    walk_items<NT, E>(sm, pr, n, sg, kn, mkA & 31u, mkB & 31u,
+                      [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes, bool long_run) {
+                        const uint32_t m = inB ? mkB : mkA;
+                        bool emit;
+                        const Token t = make_token(m >> 5, m & 31u, u, k, is_zero, closes, long_run, &emit);
+                        if (emit) my_bits += (u64)t.hlen + t.q + t.tlen;
+                      });
+    u64 tok_total;
+    const u64 my_ex = block_excl_scan_u64<NT>(my_bits, sm.Scr(), &tok_total);
+    __syncthreads();
+    const uint32_t hdr_fixed = 16u + (type == PRED_LPC ? 16u * order : 0u) + 8u;
+    const u64 hdr_bits = (u64)hdr_fixed + 7ull * nparts;
+    const u64 total_bits = hdr_bits + tok_total;
+    const u64 total_bytes = (total_bits + 7ull) >> 3;  // == rec->bytes by construction
+
+    // windows over the absolute bit range of this channel-block, aligned to destination words
+    uint32_t* stg = reinterpret_cast<uint32_t*>(sm.X());
+    constexpr uint32_t W = ASmem<NT, E>::CAP;  // words per window
+    const u64 abs0 = out_off * 8ull;           // absolute bit address of the first bit
+    const u64 absEnd = abs0 + total_bytes * 8ull;
+    for (u64 wstart = abs0 & ~31ull; wstart < absEnd; wstart += (u64)W * 32ull) {
+      for (uint32_t i = tid; i < W; i += NT) stg[i] = 0u;
+      __syncthreads();
+      const i64 rel0 = (i64)(abs0 - wstart);  // staging position of bit 0 of the channel-block (may be negative)
+      // header
+      if (tid == 0u) {
+        or_field(stg, W, rel0, type, 8u);
+        or_field(stg, W, rel0 + 8, order, 8u);
+        if (type == PRED_LPC)
+          for (uint32_t i = 1; i <= order; ++i) or_field(stg, W, rel0 + 16 + 16 * (i64)(i - 1u), (uint16_t)rec->coef[i], 16u);
+        const uint32_t m0 = sm.SelMK()[nparts - 1u] >> 5;
+        const uint32_t control = ((m0 & 3u) << 5) | (p ? (0x80u | p) : 0u);  // block/encoder.cpp:773-778
+        or_field(stg, W, rel0 + (i64)hdr_fixed - 8, control, 8u);
+      }
+      for (uint32_t s = tid; s < nparts; s += NT) {
+        const uint32_t mk = sm.SelMK()[nparts - 1u + s];
+        or_field(stg, W, rel0 + (i64)hdr_fixed + 7 * (i64)s, ((mk >> 5) << 5) | (mk & 31u), 7u);
+      }
+      // tokens
+      const i64 t0 = rel0 + (i64)hdr_bits + (i64)my_ex;
+      if (my_bits && t0 < (i64)W * 32 && t0 + (i64)my_bits > 0) {
+        i64 pos = t0;
+        walk_items<NT, E>(sm, pr, n, sg, kn, mkA & 31u, mkB & 31u,
+                          [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
+                              bool long_run) {
+                            const uint32_t m = inB ? mkB : mkA;
+                            bool emit;
+                            const Token t = make_token(m >> 5, m & 31u, u, k, is_zero, closes, long_run, &emit);
+                            if (!emit) return;
+                            or_field(stg, W, pos, t.head, t.hlen);
+                            or_ones(stg, W, pos + t.hlen, t.q);
+                            or_field(stg, W, pos + t.hlen + t.q, t.tail, t.tlen);
+                            pos += (i64)t.hlen + t.q + t.tlen;
+                          });
+      }
+      __syncthreads();
+      // copy out: staging word i <-> destination bytes [wstart/8 + 4i, +4)
+      const u64 wbyte0 = wstart >> 3;
+      const u64 lo = out_off, hi = out_off + total_bytes;
+      for (uint32_t i = tid; i < W; i += NT) {
+        const u64 b0 = wbyte0 + 4ull * i;
+        if (b0 >= hi) break;
+        if (b0 + 4ull <= lo) continue;
+        const uint32_t v = stg[i];
+        if (b0 >= lo && b0 + 4ull <= hi) {
+          *reinterpret_cast<uint32_t*>(payload + b0) = __byte_perm(v, 0u, 0x0123);
+        } else {
+#pragma unroll
+          for (uint32_t k = 0; k < 4u; ++k)
+            if (b0 + k >= lo && b0 + k < hi) payload[b0 + k] = (uint8_t)(v >> (24u - 8u * k));
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace lacb

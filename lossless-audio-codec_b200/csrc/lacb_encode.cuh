@@ -1,0 +1,619 @@
+// lacb_encode.cuh -- channel-block analysis and emission for the LAC encoder.
+//
+// One CTA encodes one channel-block (<= 16384 samples).  Thread t owns the E
+// consecutive samples [t*E, t*E+E); every per-sample quantity of the reference's
+// serial estimators is rewritten as a block-wide scan so nothing but the 12-step
+// Levinson recursion (done by a separate kernel) is sequential:
+//   * Block::Encoder::encode          src/codec/block/encoder.cpp:313-838
+//   * estimate_initial_k/static_k     src/codec/block/encoder.cpp:121-188  (bit-plane counts)
+//   * estimate_residual_costs         src/codec/block/encoder.cpp:201-263  (closed-form k series)
+//   * Rice::adapt_k                   src/codec/rice/rice.hpp:45-114       
+//   * LPC::compute_residual_q15       src/codec/lpc/lpc.cpp:38-61,188-229
+#pragma once
+#include "lacb_common.cuh"
+
+namespace lacb {
+
+// PCM planes resident in device memory.
+struct PcmSrc {
+  const int32_t* L;
+  const int32_t* R;  // nullptr for mono
+  u64 frames;
+};
+
+// Quantised LPC analysis of one channel-block (output of the Levinson kernel).
+struct LpcQ {
+  int16_t coef[5][13];  // candidate c = order 4+2c, coefficients 1..12 (index 0 unused)
+  int8_t used[5];       // analyze_block_q15's used_order (0 = unstable)
+  int8_t pad[5];
+};
+
+// Decision record of one channel-block: everything the emitter needs.
+struct ChanRec {
+  uint32_t bytes;      // encoded size of this channel-block (byte padded)
+  uint32_t bits;       // exact bit count before padding
+  uint8_t type;        // 0 fixed, 1 FIR, 2 LPC
+  uint8_t order;       // order byte as written
+  uint8_t p;           // partition order
+  uint8_t taps;        // taps actually used for the residual (LPC: used_order)
+  int16_t coef[13];    // Q15 coefficients 1..order (LPC)
+  uint8_t part[256];   // (mode << 5) | k per partition
+  uint16_t pad;
+  uint32_t cand_lo[11];  // debug: low 32 bits of every candidate's best_bits (0xFFFFFFFF = skipped)
+};
+
+__device__ __forceinline__ int32_t load_sample(const PcmSrc& s, int kind, u64 idx) {
+  // kind: 0 left/mono, 1 right, 2 mid, 3 side (simd/neon.cpp:14-30: wrapping add, arithmetic >> 1)
+  const int32_t l = s.L[idx];
+  if (kind == 0) return l;
+  const int32_t r = s.R[idx];
+  if (kind == 1) return r;
+  if (kind == 2) return (int32_t)((uint32_t)l + (uint32_t)r) >> 1;
+  return (int32_t)((uint32_t)l - (uint32_t)r);
+}
+
+// partition geometry, block/encoder.cpp:93-119
+__device__ __forceinline__ uint32_t max_partition_order(uint32_t n) {
+  uint32_t mp = 0;
+  for (uint32_t p = 1; p <= kMaxPartOrder; ++p) {
+    if ((n >> p) < kMinPart) break;
+    mp = p;
+  }
+  return mp;
+}
+
+struct AMisc {
+  u64 tot_rice, tot_zr, tot_bin, u_total, p_first, stat_bits, red64;
+  uint32_t cnt_tot[8], cnt_first[8];
+  uint32_t k_init, k_stat, has_run, red32;
+  uint32_t hasrun_bits[8];
+};
+
+template <int NT, int E>
+struct ASmem {
+  static constexpr uint32_t CAP = NT * E;
+  static constexpr uint32_t MAXSEG = 511;
+  static constexpr size_t oX = 0;
+  static constexpr size_t oU = oX + (size_t)CAP * 4;
+  static constexpr size_t oPthr = oU + (size_t)CAP * 4;
+  static constexpr size_t oCpre = oPthr + (((size_t)(NT + 1) * 8 + 15) & ~(size_t)15);
+  static constexpr size_t oFlg = oCpre + (size_t)(NT + 1) * 32;
+  static constexpr size_t oKpub = oFlg + (size_t)NT * 4;
+  static constexpr size_t oScr = oKpub + (size_t)NT * 4;
+  static constexpr size_t oSegP = oScr + 40 * 8;
+  static constexpr size_t oSegStat = oSegP + (MAXSEG + 1) * 8;
+  static constexpr size_t oSelBits = oSegStat + (MAXSEG + 1) * 8;
+  static constexpr size_t oFb = oSelBits + (MAXSEG + 1) * 8;
+  static constexpr size_t oMisc = oFb + 3 * 258 * 8;
+  static constexpr size_t oSegK = oMisc + ((sizeof(AMisc) + 15) & ~(size_t)15);
+  static constexpr size_t oSelMK = oSegK + (MAXSEG + 1) * 2;
+  static constexpr size_t BYTES = oSelMK + (MAXSEG + 1);
+
+  unsigned char* base;
+  __device__ int32_t* X() const { return reinterpret_cast<int32_t*>(base + oX); }
+  __device__ uint32_t* U() const { return reinterpret_cast<uint32_t*>(base + oU); }
+  __device__ u64* Pthr() const { return reinterpret_cast<u64*>(base + oPthr); }
+  __device__ PlaneCounts* Cpre() const { return reinterpret_cast<PlaneCounts*>(base + oCpre); }
+  __device__ uint32_t* Flg() const { return reinterpret_cast<uint32_t*>(base + oFlg); }
+  __device__ uint32_t* Kpub() const { return reinterpret_cast<uint32_t*>(base + oKpub); }
+  __device__ u64* Scr() const { return reinterpret_cast<u64*>(base + oScr); }
+  __device__ u64* SegP() const { return reinterpret_cast<u64*>(base + oSegP); }
+  __device__ u64* SegStat() const { return reinterpret_cast<u64*>(base + oSegStat); }
+  __device__ u64* SelBits() const { return reinterpret_cast<u64*>(base + oSelBits); }
+  __device__ u64* Fb() const { return reinterpret_cast<u64*>(base + oFb); }
+  __device__ AMisc* Misc() const { return reinterpret_cast<AMisc*>(base + oMisc); }
+  __device__ uint16_t* SegK() const { return reinterpret_cast<uint16_t*>(base + oSegK); }
+  __device__ uint8_t* SelMK() const { return reinterpret_cast<uint8_t*>(base + oSelMK); }
+};
+
+// ---------------------------------------------------------------------------
+// load the channel-block into the swizzled X plane (zero padded to CAP)
+template <int NT, int E>
+__device__ __forceinline__ void load_block(const ASmem<NT, E>& sm, const PcmSrc& src, int kind, u64 start,
+                                           uint32_t n) {
+  int32_t* X = sm.X();
+  for (uint32_t i = threadIdx.x; i < ASmem<NT, E>::CAP; i += NT) {
+    int32_t v = 0;
+    if (i < n) v = load_sample(src, kind, start + i);
+    X[swz(i)] = v;
+  }
+}
+
+// x[0..11] = the 12 samples before the thread's chunk (zero before the block start),
+// x[12..12+E) = the thread's own samples
+template <int NT, int E>
+__device__ __forceinline__ void load_items(const ASmem<NT, E>& sm, int32_t (&x)[E + 12]) {
+  const int4* X4 = reinterpret_cast<const int4*>(sm.X());
+  const int q0 = (int)threadIdx.x * (E / 4);
+#pragma unroll
+  for (int c = -3; c < E / 4; ++c) {
+    int4 v = make_int4(0, 0, 0, 0);
+    if (q0 + c >= 0) v = X4[swz_chunk((uint32_t)(q0 + c))];
+    x[12 + 4 * c + 0] = v.x;
+    x[12 + 4 * c + 1] = v.y;
+    x[12 + 4 * c + 2] = v.z;
+    x[12 + 4 * c + 3] = v.w;
+  }
+}
+
+// Fixed / FIR residuals, block/encoder.cpp:265-309.  The fixed predictors are exact
+// in wrapping 32-bit arithmetic (the reference truncates the int64 difference).
+template <int E>
+__device__ __forceinline__ void residual_fixed(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n, int order,
+                                               int32_t (&r)[E]) {
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const uint32_t idx = g0 + j;
+    const uint32_t x0 = (uint32_t)x[12 + j], x1 = (uint32_t)x[11 + j], x2 = (uint32_t)x[10 + j],
+                   x3 = (uint32_t)x[9 + j], x4 = (uint32_t)x[8 + j];
+    uint32_t v;
+    switch (order) {
+      case 1: v = x0 - x1; break;
+      case 2: v = x0 - 2u * x1 + x2; break;
+      case 3: v = x0 - 3u * x1 + 3u * x2 - x3; break;
+      case 4: v = x0 - 4u * x1 + 6u * x2 - 4u * x3 + x4; break;
+      default: v = x0; break;
+    }
+    if (idx < (uint32_t)order) v = x0;
+    r[j] = idx < n ? (int32_t)v : 0;
+  }
+}
+template <int E>
+__device__ __forceinline__ void residual_fir(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n, int32_t (&r)[E]) {
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const uint32_t idx = g0 + j;
+    const i64 p = (3ll * (i64)x[11 + j] - (i64)x[10 + j]) >> 2;
+    uint32_t v = (uint32_t)(u64)((i64)x[12 + j] - p);
+    if (idx < 2u) v = (uint32_t)x[12 + j];
+    r[j] = idx < n ? (int32_t)v : 0;
+  }
+}
+// LPC residual with `TAPS` Q15 taps, lpc.cpp:38-61; returns true if any residual leaves int32
+template <int E, int TAPS>
+__device__ __forceinline__ bool residual_lpc_t(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n,
+                                               const int16_t* c, int32_t (&r)[E]) {
+  int32_t cf[TAPS + 1];
+#pragma unroll
+  for (int t = 1; t <= TAPS; ++t) cf[t] = c[t];
+  bool ovf = false;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    i64 acc = 0;
+#pragma unroll
+    for (int t = 1; t <= TAPS; ++t) acc += (i64)cf[t] * (i64)x[12 + j - t];
+    const i64 d = (i64)x[12 + j] - (acc >> 15);
+    const bool in = g0 + j < n;
+    if (in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
+    r[j] = in ? (int32_t)d : 0;
+  }
+  return ovf;
+}
+template <int E>
+__device__ __forceinline__ bool residual_lpc(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n,
+                                             const int16_t* c, int taps, int32_t (&r)[E]) {
+  switch (taps) {
+    case 4: return residual_lpc_t<E, 4>(x, g0, n, c, r);
+    case 6: return residual_lpc_t<E, 6>(x, g0, n, c, r);
+    case 8: return residual_lpc_t<E, 8>(x, g0, n, c, r);
+    case 10: return residual_lpc_t<E, 10>(x, g0, n, c, r);
+    case 12: return residual_lpc_t<E, 12>(x, g0, n, c, r);
+    default: break;
+  }
+  // odd / short orders (Levinson stopped early): generic, coefficients past `taps` ignored
+  bool ovf = false;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    i64 acc = 0;
+#pragma unroll
+    for (int t = 1; t <= 12; ++t)
+      if (t <= taps) acc += (i64)c[t] * (i64)x[12 + j - t];
+    const i64 d = (i64)x[12 + j] - (acc >> 15);
+    const bool in = g0 + j < n;
+    if (in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
+    r[j] = in ? (int32_t)d : 0;
+  }
+  return ovf;
+}
+
+// ---------------------------------------------------------------------------
+// Per-residual preparation: zig-zag, U plane, per-thread prefix of u, last-nonzero
+// scan and bit-plane counts (totals only, or the full per-thread prefix for the
+// partition search when FULL).
+template <int NT, int E>
+struct Prep {
+  uint32_t u[E];
+  u64 Pex;          // sum of u over all samples before this thread's chunk
+  int32_t lnz_ex;   // index of the last non-zero residual before the chunk (-1: none)
+  uint32_t zmask;   // bit j: sample g0+j exists and its residual is zero
+};
+
+template <int NT, int E, bool FULL>
+__device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&r)[E], uint32_t n, Prep<NT, E>& pr) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  AMisc* mi = sm.Misc();
+  u64 S = 0;
+  int32_t lastnz = -1;
+  uint32_t zmask = 0;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const bool in = g0 + j < n;
+    const uint32_t uu = in ? zz32(r[j]) : 0u;
+    pr.u[j] = uu;
+    S += uu;
+    if (uu) lastnz = (int32_t)(g0 + j);
+    if (in && uu == 0u) zmask |= 1u << j;
+  }
+  pr.zmask = zmask;
+  uint4* U4 = reinterpret_cast<uint4*>(sm.U());
+#pragma unroll
+  for (int c = 0; c < E / 4; ++c)
+    U4[swz_chunk(tid * (E / 4) + c)] = make_uint4(pr.u[4 * c], pr.u[4 * c + 1], pr.u[4 * c + 2], pr.u[4 * c + 3]);
+  if (!FULL && tid < 8) {
+    mi->cnt_tot[tid] = 0u;
+    mi->cnt_first[tid] = 0u;
+  }
+  __syncthreads();
+  u64 total;
+  pr.Pex = block_excl_scan_u64<NT>(S, sm.Scr(), &total);
+  sm.Pthr()[tid] = pr.Pex;
+  if (tid == 0) {
+    sm.Pthr()[NT] = total;
+    mi->u_total = total;
+    if (NT * E <= 256) mi->p_first = total;
+  }
+  if (NT * E > 256 && g0 == 256u) mi->p_first = pr.Pex;
+  pr.lnz_ex = block_excl_max_i32<NT>(lastnz, reinterpret_cast<int32_t*>(sm.Scr()));
+
+  uint32_t V[5];
+  csa_count<E>(pr.u, V);
+  PlaneCounts pc;
+  planes_from_sliced(V, pc);
+  if (FULL) {
+    PlaneCounts* Cp = sm.Cpre();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      uint32_t tot;
+      const uint32_t ex = block_excl_scan_u32<NT>(pc.w[w], reinterpret_cast<uint32_t*>(sm.Scr()), &tot);
+      Cp[tid].w[w] = ex;
+      if (tid == 0) Cp[NT].w[w] = tot;
+    }
+  } else {
+    const bool first = g0 < 256u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const uint32_t t = warp_sum_u32(pc.w[w]);
+      if ((tid & 31u) == 0u && t) atomicAdd(&mi->cnt_tot[w], t);
+      if ((tid >> 5) * 32u * E < 256u) {  // warp-uniform: this warp overlaps the first 256 samples
+        const uint32_t f = warp_sum_u32(first ? pc.w[w] : 0u);
+        if ((tid & 31u) == 0u && f) atomicAdd(&mi->cnt_first[w], f);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// prefix of u / of the plane counts at an arbitrary sample position (any thread)
+template <int NT, int E>
+__device__ __forceinline__ u64 prefix_u(const ASmem<NT, E>& sm, uint32_t pos) {
+  const uint32_t t = pos / E, rem = pos - t * E;
+  u64 v = sm.Pthr()[t];
+  const uint32_t* U = sm.U();
+  for (uint32_t m = 0; m < rem; ++m) v += U[swz(t * E + m)];
+  return v;
+}
+template <int NT, int E>
+__device__ __forceinline__ void prefix_counts(const ASmem<NT, E>& sm, uint32_t pos, PlaneCounts& pc) {
+  const uint32_t t = pos / E, rem = pos - t * E;
+  pc = sm.Cpre()[t];
+  const uint32_t* U = sm.U();
+  for (uint32_t m = 0; m < rem; ++m) planes_add_value(pc, U[swz(t * E + m)]);
+}
+
+// ---------------------------------------------------------------------------
+// Segment geometry of one thread at partition level p (p == 0: whole block).
+struct SegGeom {
+  uint32_t sidA;   // table index of the segment holding the first item
+  uint32_t a0;     // its first sample
+  uint32_t bnd;    // first sample of the next segment (0xFFFFFFFF when none)
+  uint32_t s0;     // segment number inside the level
+};
+__device__ __forceinline__ SegGeom seg_geom(uint32_t g0, uint32_t n, uint32_t p) {
+  SegGeom g;
+  if (p == 0u) {
+    g.sidA = 0u;
+    g.a0 = 0u;
+    g.bnd = 0xFFFFFFFFu;
+    g.s0 = 0u;
+    return g;
+  }
+  const uint32_t base = n >> p, cnt = 1u << p;
+  uint32_t s0 = g0 / base;
+  if (s0 > cnt - 1u) s0 = cnt - 1u;
+  g.s0 = s0;
+  g.sidA = cnt - 1u + s0;
+  g.a0 = s0 * base;
+  g.bnd = (s0 + 1u < cnt) ? g.a0 + base : 0xFFFFFFFFu;
+  return g;
+}
+
+// k series of one level: on return kn[j] is the Rice parameter the model yields
+// AFTER consuming sample g0+j (i.e. the k used for sample g0+j+1 unless that sample
+// starts a segment), and Kpub[tid] = kn[E-1].
+//   STATEFUL  : Rice::adapt_k with drift and micro windows (rice.hpp:45-114), p = 0
+//   !STATEFUL : adapt_k_stateless (block/encoder.cpp:72-77), restarted per segment
+template <int NT, int E, bool STATEFUL>
+__device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                         const SegGeom& sg, uint8_t (&kn)[E]) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const u64 PaA = STATEFUL ? 0ull : sm.SegP()[sg.sidA];
+  const u64 PaB = (!STATEFUL && sg.bnd != 0xFFFFFFFFu) ? sm.SegP()[sg.sidA + 1u] : 0ull;
+  u64 Pin = pr.Pex;
+  uint32_t hint = 0u;
+  uint32_t flg = 0u;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const uint32_t idx = g0 + j;
+    Pin += pr.u[j];
+    const bool inB = idx >= sg.bnd;
+    const uint32_t a = inB ? sg.bnd : sg.a0;
+    const uint32_t c = idx - a + 1u;
+    const u64 N = Pin - (inB ? PaB : PaA) + (c >> 1);
+    if (j == 0 || (inB && idx == sg.bnd)) hint = kbase_guess(N, c);
+    const uint32_t kb = kbase_from(N, c, hint);
+    hint = kb;
+    kn[j] = (uint8_t)kb;
+    if (STATEFUL) {
+      const uint32_t q = (kb >= 31u) ? 0u : (pr.u[j] >> kb);
+      if (idx < n) flg |= ((q > 3u) ? (1u << j) : 0u) | ((q == 0u) ? (1u << (16 + j)) : 0u);
+    }
+  }
+  if (STATEFUL) {
+    uint32_t* Flg = sm.Flg();
+    Flg[tid] = flg;
+    __syncthreads();
+    constexpr int D = (int)kMicroWin / E;       // threads spanned by the 96-sample micro window
+    constexpr int DW = (int)kDriftWin / E;      // threads spanned by the 256-sample drift window
+    uint32_t fullL = 0u, fullZ = 0u;
+#pragma unroll
+    for (int d = 1; d < D; ++d) {
+      const uint32_t w = ((int)tid - d >= 0) ? Flg[tid - d] : 0u;
+      fullL += (uint32_t)__popc(w & 0xFFFFu);
+      fullZ += (uint32_t)__popc(w >> 16);
+    }
+    const uint32_t part = ((int)tid - D >= 0) ? Flg[tid - D] : 0u;
+    const int tt = (int)tid - DW;
+    u64 wprev = tt >= 0 ? sm.Pthr()[tt] : 0ull;  // becomes the inclusive prefix at item j of thread tt
+    const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
+    Pin = pr.Pex;
+    uint32_t uw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const uint32_t idx = g0 + j;
+      const uint32_t c = idx + 1u;
+      Pin += pr.u[j];
+      if ((j & 3) == 0) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (tt >= 0) v = U4[swz_chunk((uint32_t)tt * (E / 4) + (uint32_t)(j >> 2))];
+        uw[0] = v.x; uw[1] = v.y; uw[2] = v.z; uw[3] = v.w;
+      }
+      wprev += uw[j & 3];
+      const u64 N = Pin + (c >> 1);
+      const uint32_t kb = kn[j];
+      int bias = 0;
+      if (c >= kDriftWin && N >= (u64)c) {
+        const u64 ws = Pin - wprev;          // sum of the last 256 u (wprev == 0 when tt < 0, c == 256)
+        const u64 lm = (ws + 128ull) >> 8;
+        const u64 tA = (3ull * lm + 3ull) >> 2;
+        if (N < tA * c) {
+          bias = 1;
+        } else {
+          const u64 tB = lm + 1ull + lm / 3ull;
+          if (N >= tB * c) bias = -1;
+        }
+      }
+      if (c >= kMicroWin) {
+        const uint32_t low = (2u << j) - 1u;                 // items 0..j
+        const uint32_t high = (~low) & ((1u << E) - 1u);     // items j+1..E-1
+        const uint32_t L = fullL + (uint32_t)__popc(flg & low) + (uint32_t)__popc(part & high);
+        const uint32_t Z = fullZ + (uint32_t)__popc((flg >> 16) & low) + (uint32_t)__popc((part >> 16) & high);
+        if (L * 4u >= 288u) bias = bias + 1 < 1 ? bias + 1 : 1;
+        else if (Z * 5u >= 384u) bias = bias - 1 > -1 ? bias - 1 : -1;
+      }
+      int k = (int)kb + bias;
+      k = k < 0 ? 0 : (k > 31 ? 31 : k);
+      kn[j] = (uint8_t)k;
+    }
+  }
+  sm.Kpub()[tid] = kn[E - 1];
+  __syncthreads();
+}
+
+// Zero mask of the thread's E samples plus the next 4 (look-ahead for run detection),
+// clipped to the block end.
+template <int NT, int E>
+__device__ __forceinline__ uint32_t zero_lookahead(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  uint32_t zm = pr.zmask;
+  if (tid + 1u < (uint32_t)NT) {
+    const uint4 v = reinterpret_cast<const uint4*>(sm.U())[swz_chunk((tid + 1u) * (E / 4))];
+    const uint32_t nx = g0 + E;
+    if (nx + 0u < n && v.x == 0u) zm |= 1u << (E + 0);
+    if (nx + 1u < n && v.y == 0u) zm |= 1u << (E + 1);
+    if (nx + 2u < n && v.z == 0u) zm |= 1u << (E + 2);
+    if (nx + 3u < n && v.w == 0u) zm |= 1u << (E + 3);
+  }
+  return zm;
+}
+
+// Token of one sample under (mode, k): head bits, unary quotient, tail bits.
+// Emission rules, block/encoder.cpp:585-771 with Rice::encode (rice.cpp:17-32) for the
+// signed codes and write_rice_unsigned (encoder.cpp:79-87) for static / run lengths.
+struct Token {
+  uint32_t head, hlen;  // <= 3 bits
+  uint32_t q;           // unary ones
+  uint32_t tail, tlen;  // terminator + remainder, or a raw field (<= 32 bits)
+};
+__device__ __forceinline__ Token token_rice_signed(uint32_t u, uint32_t k, uint32_t head, uint32_t hlen) {
+  Token t;
+  t.head = head;
+  t.hlen = hlen;
+  t.q = u >> k;  // k <= 31 here (Rice::encode guards k >= 32 only)
+  t.tail = k ? (u & ((1u << k) - 1u)) : 0u;
+  t.tlen = k + 1u;  // the 0 terminator is the tail's leading bit
+  return t;
+}
+__device__ __forceinline__ Token token_rice_unsigned(uint32_t u, uint32_t k, uint32_t head, uint32_t hlen) {
+  Token t;
+  t.head = head;
+  t.hlen = hlen;
+  t.q = (k >= 31u) ? 0u : (u >> k);
+  t.tail = k ? (u & ((1u << k) - 1u)) : 0u;
+  t.tlen = k + 1u;
+  return t;
+}
+
+// Walks the thread's samples with the k series in place and calls
+//   f(j, idx, inB, u, k, is_zero, run_len_if_last /*0 unless this sample closes a run >= 4*/, in_long_run)
+template <int NT, int E, typename F>
+__device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                           const SegGeom& sg, const uint8_t (&kn)[E], uint32_t kinitA,
+                                           uint32_t kinitB, F&& f) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  if (g0 >= n) return;
+  const uint32_t zm_all = zero_lookahead(sm, pr, n);
+  // samples at or after the segment boundary do not extend a run that started before it
+  uint32_t zmA = zm_all;
+  if (sg.bnd != 0xFFFFFFFFu && sg.bnd - g0 < (uint32_t)(E + 4)) zmA &= (1u << (sg.bnd - g0)) - 1u;
+  uint32_t z;  // zeros immediately before g0 inside the current segment
+  {
+    const uint32_t byscan = g0 - 1u - (uint32_t)pr.lnz_ex;  // lnz_ex >= -1
+    const uint32_t byseg = g0 - sg.a0;
+    z = byscan < byseg ? byscan : byseg;
+  }
+  uint32_t kprev = tid ? sm.Kpub()[tid - 1u] : 0u;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const uint32_t idx = g0 + j;
+    if (idx < n) {
+      const bool inB = idx >= sg.bnd;
+      uint32_t k = (j == 0) ? kprev : (uint32_t)kn[j - 1];
+      if (idx == sg.a0) { k = kinitA; z = 0u; }
+      if (idx == sg.bnd) { k = kinitB; z = 0u; }
+      const uint32_t zm = inB ? zm_all : zmA;
+      const bool is_zero = (zm >> j) & 1u;
+      z = is_zero ? z + 1u : 0u;
+      // zeros following this sample inside the segment, at most 4 looked at
+      const uint32_t fwd = (uint32_t)__ffs((int)~(zm >> (j + 1))) - 1u;
+      const bool long_run = is_zero && (z + fwd >= kZrMinRun);
+      const uint32_t closes = (long_run && fwd == 0u) ? z : 0u;
+      f(j, idx, inB, pr.u[j], k, is_zero, closes, long_run);
+    }
+  }
+}
+
+// estimate_residual_costs (block/encoder.cpp:201-263) for one level.  STATEFUL writes
+// block totals to AMisc; otherwise per-segment prefix values go to Fb (3 x 258) and
+// the has-run bits to AMisc::hasrun_bits.
+template <int NT, int E, bool STATEFUL>
+__device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t p,
+                                          uint32_t kinit_stateful) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  AMisc* mi = sm.Misc();
+  const SegGeom sg = seg_geom(g0, n, STATEFUL ? 0u : p);
+  uint8_t kn[E];
+  if (tid == 0) {
+    mi->tot_rice = 0ull;
+    mi->tot_zr = 0ull;
+    mi->tot_bin = 0ull;
+  }
+  if (tid < 8) mi->hasrun_bits[tid] = 0u;
+  k_series<NT, E, STATEFUL>(sm, pr, n, sg, kn);  // ends with a barrier
+  uint32_t kinitA, kinitB = 0u;
+  if (STATEFUL) {
+    kinitA = kinit_stateful;
+  } else {
+    kinitA = sm.SegK()[sg.sidA] & 0xFFu;
+    if (sg.bnd != 0xFFFFFFFFu) kinitB = sm.SegK()[sg.sidA + 1u] & 0xFFu;
+  }
+  u64 riceA = 0, zrA = 0, binA = 0, riceB = 0, zrB = 0, binB = 0;
+  uint32_t runA = 0, runB = 0;
+  walk_items<NT, E>(sm, pr, n, sg, kn, kinitA, kinitB,
+                    [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
+                        bool long_run) {
+                      const u64 rc = rice_cost(u, k);
+                      u64 bin, zr;
+                      if (is_zero) bin = 2ull;
+                      else if (u <= 4u) bin = 3ull;
+                      else bin = 2ull + rc;
+                      if (!is_zero) {
+                        const uint32_t esc = 1u << (k + 3u < 24u ? k + 3u : 24u);
+                        zr = 2ull + ((u > esc) ? 32ull : rc);
+                      } else if (long_run) {
+                        zr = closes ? 2ull + rice_cost(closes - kZrMinRun, kZrRunK) : 0ull;
+                      } else {
+                        zr = 2ull + rc;
+                      }
+                      if (inB) { riceB += rc; zrB += zr; binB += bin; runB |= (closes != 0u); }
+                      else { riceA += rc; zrA += zr; binA += bin; runA |= (closes != 0u); }
+                    });
+  if (STATEFUL) {
+    const u64 r = warp_sum_u64(riceA), z = warp_sum_u64(zrA), b = warp_sum_u64(binA);
+    if ((tid & 31u) == 0u) {
+      atomicAdd(&mi->tot_rice, r);
+      atomicAdd(&mi->tot_zr, z);
+      atomicAdd(&mi->tot_bin, b);
+    }
+    const int any = __syncthreads_or((int)runA);
+    if (tid == 0) mi->has_run = (uint32_t)any;
+    __syncthreads();
+  } else {
+    u64* Fb = sm.Fb();
+    const uint32_t cnt = 1u << p;
+    u64 tot;
+    const bool ownsA = (sg.a0 == g0);                                  // segment starts exactly at this thread
+    const bool ownsB = (sg.bnd != 0xFFFFFFFFu && sg.bnd - g0 < (uint32_t)E && sg.bnd > g0);
+    u64 ex = block_excl_scan_u64<NT>(riceA + riceB, sm.Scr(), &tot);
+    if (ownsA) Fb[sg.s0] = ex;
+    if (ownsB) Fb[sg.s0 + 1u] = ex + riceA;
+    if (tid == 0) Fb[cnt] = tot;
+    ex = block_excl_scan_u64<NT>(zrA + zrB, sm.Scr(), &tot);
+    if (ownsA) Fb[258 + sg.s0] = ex;
+    if (ownsB) Fb[258 + sg.s0 + 1u] = ex + zrA;
+    if (tid == 0) Fb[258 + cnt] = tot;
+    ex = block_excl_scan_u64<NT>(binA + binB, sm.Scr(), &tot);
+    if (ownsA) Fb[516 + sg.s0] = ex;
+    if (ownsB) Fb[516 + sg.s0 + 1u] = ex + binA;
+    if (tid == 0) Fb[516 + cnt] = tot;
+    if (runA) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
+    if (runB) atomicOr(&mi->hasrun_bits[(sg.s0 + 1u) >> 5], 1u << ((sg.s0 + 1u) & 31u));
+    __syncthreads();
+  }
+}
+
+// Exact emitted bit count of the thread's samples for the final decision.
+// part_mk[s] = (mode << 5) | k of segment s at level p.
+__device__ __forceinline__ Token make_token(uint32_t mode, uint32_t kstatic, uint32_t u, uint32_t k, bool is_zero,
+                                            uint32_t closes, bool long_run, bool* emit) {
+  *emit = true;
+  if (mode == MODE_RICE) return token_rice_signed(u, k, 0u, 0u);
+  if (mode == MODE_STATIC) return token_rice_unsigned(u, kstatic, 0u, 0u);
+  if (mode == MODE_BIN) {
+    Token t;
+    t.q = 0u;
+    if (is_zero) { t.head = 0u; t.hlen = 2u; t.tail = 0u; t.tlen = 0u; return t; }
+    if (u <= 2u) { t.head = (1u << 1) | (u & 1u); t.hlen = 3u; t.tail = 0u; t.tlen = 0u; return t; }   // +-1: tag 01 + sign
+    if (u <= 4u) { t.head = (2u << 1) | (u & 1u); t.hlen = 3u; t.tail = 0u; t.tlen = 0u; return t; }   // +-2: tag 10 + sign
+    return token_rice_signed(u, k, 3u, 2u);
+  }
+  // zero-run mode
+  if (is_zero && long_run) {
+    if (!closes) { *emit = false; Token t = {0u, 0u, 0u, 0u, 0u}; return t; }
+    return token_rice_unsigned(closes - kZrMinRun, kZrRunK, 1u, 2u);
+  }
+  const uint32_t esc = 1u << (k + 3u < 24u ? k + 3u : 24u);
+  if (u > esc) { Token t; t.head = 2u; t.hlen = 2u; t.q = 0u; t.tail = u; t.tlen = 32u; return t; }
+  return token_rice_signed(u, k, 0u, 2u);
+}
+
+}  // namespace lacb
