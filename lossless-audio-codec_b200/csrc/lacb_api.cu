@@ -99,7 +99,7 @@ template <typename T>
 T* as(DevBuf& b) {
   return reinterpret_cast<T*>(b.p);
 }
-uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+uint32_t lacb_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 // Device part of the encoder: planes already on the device.  On success the payload is
 // in ctx->payload, the per-block sizes in ctx->blk_bytes, *total the payload size.
@@ -137,7 +137,7 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
   CK(cudaMemsetAsync(ctx->misc.p, 0, 64, st));
   CK(cudaMemsetAsync(ctx->counts.p, 0, 64, st));
 
-  const uint32_t wide = umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 8u);
+  const uint32_t wide = lacb_umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 8u);
   if (validate) {
     auto kv = k_validate;
     LACB_LAUNCH(kv, wide ? wide : 1u, 256, 0, st, src, prm->bit_depth, miscw);
@@ -147,25 +147,25 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
   // stereo decision (mode 2): proxy, then 3x256-sample probes for the uncertain blocks
   if (automs) {
     auto kp = k_stereo_proxy;
-    LACB_LAUNCH(kp, umin(nb, (uint32_t)ctx->sms * 8u), 256, 0, st, src, cfg, as<uint32_t>(ctx->flags));
+    LACB_LAUNCH(kp, lacb_umin(nb, (uint32_t)ctx->sms * 8u), 256, 0, st, src, cfg, as<uint32_t>(ctx->flags));
     auto kb = k_build_jobs<true>;
     LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs_p), counts + 1);
-    const uint32_t pgrid = umin(nb * 12u, (uint32_t)ctx->sms * 16u);
+    const uint32_t pgrid = lacb_umin(nb * 12u, (uint32_t)ctx->sms * 16u);
     auto ka = k_autocorr<PROBE_NT, PROBE_E, true>;
     LACB_LAUNCH(ka, pgrid, PROBE_NT, PROBE_NT * PROBE_E * 4, st, src, as<uint32_t>(ctx->jobs_p), counts + 1,
                 as<i64>(ctx->acor_p));
     auto kl = k_levinson<true>;
-    LACB_LAUNCH(kl, umin((nb * 12u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs_p),
+    LACB_LAUNCH(kl, lacb_umin((nb * 12u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs_p),
                 counts + 1, as<i64>(ctx->acor_p), as<LpcQ>(ctx->lpcq_p));
     auto kz = k_analyze<PROBE_NT, PROBE_E, true>;
     LACB_LAUNCH(kz, pgrid, PROBE_NT, kProbeSmem, st, src, cfg, as<uint32_t>(ctx->jobs_p),
                 counts + 1, as<LpcQ>(ctx->lpcq_p), (ChanRec*)nullptr, as<uint32_t>(ctx->probe_bytes));
     auto kd = k_decide_probes;
-    LACB_LAUNCH(kd, umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags),
+    LACB_LAUNCH(kd, lacb_umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags),
                 as<uint32_t>(ctx->probe_bytes));
   } else {
     auto kf = k_plan_fixed;
-    LACB_LAUNCH(kf, umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags));
+    LACB_LAUNCH(kf, lacb_umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags));
   }
   CK(cudaEventRecord(ctx->ev[EV_STEREO], st));
 
@@ -173,12 +173,12 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
   {
     auto kb = k_build_jobs<false>;
     LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs), counts);
-    const uint32_t fgrid = umin(nb * 4u, (uint32_t)ctx->sms);
+    const uint32_t fgrid = lacb_umin(nb * 4u, (uint32_t)ctx->sms);
     auto ka = k_autocorr<FULL_NT, FULL_E, false>;
     LACB_LAUNCH(ka, fgrid, FULL_NT, FULL_NT * FULL_E * 4, st, src, as<uint32_t>(ctx->jobs), counts,
                 as<i64>(ctx->acor));
     auto kl = k_levinson<false>;
-    LACB_LAUNCH(kl, umin((nb * 4u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs),
+    LACB_LAUNCH(kl, lacb_umin((nb * 4u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs),
                 counts, as<i64>(ctx->acor), as<LpcQ>(ctx->lpcq));
     CK(cudaEventRecord(ctx->ev[EV_LPC], st));
     auto kz = k_analyze<FULL_NT, FULL_E, false>;
@@ -214,7 +214,7 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
   CKR(ensure(ctx, ctx->payload, (size_t)tot + 8));
   {
     auto ke = k_emit<FULL_NT, FULL_E>;
-    LACB_LAUNCH(ke, umin(nb * cfg.channels, (uint32_t)ctx->sms), FULL_NT, kFullSmem, st, src, cfg,
+    LACB_LAUNCH(ke, lacb_umin(nb * cfg.channels, (uint32_t)ctx->sms), FULL_NT, kFullSmem, st, src, cfg,
                 as<uint32_t>(ctx->flags), as<ChanRec>(ctx->recs), as<u64>(ctx->blk_off), as<uint8_t>(ctx->payload));
   }
   CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
@@ -371,7 +371,7 @@ int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const voi
     CKR(ensure(ctx, ctx->packed_in, bytes + 4));
     CK(cudaMemcpyAsync(ctx->packed_in.p, pcm_a, bytes, cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(ctx->ev[EV_H2D], st));
-    const uint32_t grid = umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 16u);
+    const uint32_t grid = lacb_umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 16u);
     auto kd = k_deinterleave;
     LACB_LAUNCH(kd, grid ? grid : 1u, 256, 0, st, as<uint8_t>(ctx->packed_in), (u64)frames, prm->channels, bps,
                 as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR));
@@ -508,7 +508,7 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
               as<uint8_t>(ctx->d_ms));
   CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));
   auto kf = k_finish_pcm;
-  LACB_LAUNCH(kf, umin(n_blocks, (uint32_t)ctx->sms * 8u), 256, 0, st, cfg, as<u64>(ctx->d_fs),
+  LACB_LAUNCH(kf, lacb_umin(n_blocks, (uint32_t)ctx->sms * 8u), 256, 0, st, cfg, as<u64>(ctx->d_fs),
               as<uint32_t>(ctx->d_size), dL, dR, as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms), d_packed);
   CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
   return 0;

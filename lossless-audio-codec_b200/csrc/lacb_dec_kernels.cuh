@@ -140,7 +140,7 @@ __device__ __forceinline__ uint32_t ks_step(KState& st, uint32_t u, uint32_t old
     const u64 tA = (3ull * lm + 3ull) >> 2;
     if (N < tA * c) bias = 1;
     else {
-      const u64 tB = lm + 1ull + lm / 3ull;
+      const u64 tB = lm + 2ull + lm / 3ull;  // floor((4 lm + 3) / 3) + 1
       if (N >= tB * c) bias = -1;
     }
   }

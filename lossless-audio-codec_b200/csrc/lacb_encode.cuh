@@ -408,7 +408,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
         if (N < tA * c) {
           bias = 1;
         } else {
-          const u64 tB = lm + 1ull + lm / 3ull;
+          const u64 tB = lm + 2ull + lm / 3ull;  // floor((4 lm + 3) / 3) + 1
           if (N >= tB * c) bias = -1;
         }
       }

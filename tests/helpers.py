@@ -304,3 +304,46 @@ def stereo_corpus():
                           [np.arange((3 << 17) + 16384, (3 << 17) + 16384 + 5000)])
     c["synth24_sections"] = (sl[pick].copy(), sr[pick].copy(), 24)
     return c
+
+
+# ---------------------------------------------------------------------------
+# product bindings (lossless-audio-codec_b200/lacb.py; the directory name is not an
+# importable identifier, so it is loaded by path)
+import importlib.util as _ilu
+
+PKG_DIR = ROOT / "lossless-audio-codec_b200"
+GPU_SO = PKG_DIR / "liblac_b200.so"
+EMU_SO = ROOT / "tests" / "emu" / "liblac_b200_emu.so"
+_lacb_mod = None
+_gpu_codec = None
+_emu_codec = None
+
+
+def lacb_module():
+    global _lacb_mod
+    if _lacb_mod is None:
+        spec = _ilu.spec_from_file_location("lacb", str(PKG_DIR / "lacb.py"))
+        _lacb_mod = _ilu.module_from_spec(spec)
+        spec.loader.exec_module(_lacb_mod)
+    return _lacb_mod
+
+
+def gpu_codec():
+    """The product: nvcc-built liblac_b200.so on cuda:0.  Raises if it cannot run."""
+    global _gpu_codec
+    if _gpu_codec is None:
+        _gpu_codec = lacb_module().Codec(0, GPU_SO)
+    return _gpu_codec
+
+
+def emu_codec():
+    """TEST INFRASTRUCTURE: the same .cu sources compiled against tests/emu/cuda_emu.h
+    (CPU fiber emulator) so kernel logic can be checked where no GPU exists."""
+    global _emu_codec
+    if _emu_codec is None:
+        src = [PKG_DIR / "csrc" / f for f in os.listdir(PKG_DIR / "csrc")] + [ROOT / "tests" / "emu" / "cuda_emu.h",
+                                                                             ROOT / "tests" / "emu" / "cuda_emu.cpp"]
+        if not EMU_SO.exists() or EMU_SO.stat().st_mtime < max(p.stat().st_mtime for p in src):
+            subprocess.check_call(["make", "-s", "-C", str(PKG_DIR), "emu"])
+        _emu_codec = lacb_module().Codec(0, EMU_SO)
+    return _emu_codec
