@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- LAC block codec hot path on B200: encode + decode PCM GB/s.
+
+One "step" = one pass of the hot path over one batch: encode the batch to .lac block
+payloads, then decode those payloads back to PCM.  Workload = BASELINE.json configs[1]
+(10 min synthetic 24-bit 96 kHz stereo, forced --stereo-mode=ms) per GPU; with N GPUs
+every rank holds its own 10-minute block range of an N x 10 min file (weak scaling) and
+the only exchange is the NCCL all-gather of per-rank payload byte counts.
+
+  value : PCM bytes through encode+decode per second, PCM resident in HBM (packed WAV
+          sample bytes in, packed WAV sample bytes out), whole job over all ranks
+  e2e   : the same through the C ABI with HOST buffers (H2D of PCM / payload and D2H of
+          payload / PCM inside the timed region)
+  roofline     : the dominant kernel (encoder channel-block analysis) against measured HBM copy bandwidth
+  cpu_baseline : the reference CPU codec (oracle/_ref when built, else the C port) on the
+                 box's host cores, on a bounded slice of the same workload
+
+`--impl reference` times only the CPU codec (all host threads) on a bounded slice.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+RATE, DEPTH, CHANNELS, STEREO_MODE = 96000, 24, 2, 1
+METRIC = "encode+decode PCM throughput (BASELINE: encode & decode PCM GB/s, byte-identical .lac vs CPU ref)"
+UNIT = "GB/s"
+
+
+def synth_packed(seed: int, frames: int) -> np.ndarray:
+    """SURVEY.md Appendix C generator (tools/lac_synth.c), packed 24-bit stereo bytes."""
+    so = ROOT / "tools" / "liblac_synth.so"
+    if not so.exists():
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", str(so), str(ROOT / "tools" / "lac_synth.c")])
+    lib = C.CDLL(str(so))
+    lib.lac_synth.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lac_synth.restype = None
+    out = np.zeros(frames * CHANNELS * (DEPTH // 8), dtype=np.uint8)
+    lib.lac_synth(seed, frames, DEPTH, CHANNELS, None, None, out.ctypes.data)
+    return out
+
+
+def unpack24(pk: np.ndarray):
+    b = pk.reshape(-1, 2, 3).astype(np.int32)
+    v = b[:, :, 0] | (b[:, :, 1] << 8) | (b[:, :, 2] << 16)
+    v = (v << 8) >> 8
+    return np.ascontiguousarray(v[:, 0]), np.ascontiguousarray(v[:, 1])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_codec():
+    """(codec, kind): the compiled reference when oracle/_ref exists, else the C port."""
+    import helpers as H
+    if H.have_ref():
+        return H.ref(), "reference"
+    return H.oracle(), "port"
+
+
+def cpu_roundtrip(codec, l, r, threads):
+    t0 = time.perf_counter()
+    blob = codec.encode(l, r, RATE, DEPTH, STEREO_MODE, threads=threads)
+    t1 = time.perf_counter()
+    dl, dr, _ = codec.decode(blob, threads=threads)
+    t2 = time.perf_counter()
+    assert np.array_equal(dl, l) and np.array_equal(dr, r)
+    return t1 - t0, t2 - t1, len(blob)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    codec, kind = cpu_codec()
+    cores = os.cpu_count() or 1
+    secs = args.cpu_seconds
+    frames = RATE * secs
+    pk = synth_packed(2, frames)
+    l, r = unpack24(pk)
+    for _ in range(args.warmup):
+        cpu_roundtrip(codec, l, r, cores)
+    te = td = 0.0
+    for _ in range(args.steps):
+        a, b, _ = cpu_roundtrip(codec, l, r, cores)
+        te += a
+        td += b
+    val = pk.size * args.steps / (te + td) / 1e9
+    sample = f"first {secs} s of the workload ({pk.size / 1e6:.1f} MB PCM), encode+decode, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64", "data": "synthetic",
+        "config": workload_config(args, secs),
+        "encode_gbs": pk.size * args.steps / te / 1e9, "decode_gbs": pk.size * args.steps / td / 1e9,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def workload_config(args, secs):
+    return {"workload": f"BASELINE configs[1]: {secs} s synthetic 24-bit 96 kHz stereo WAV samples per GPU, "
+                        "forced --stereo-mode=ms, encode then decode (SURVEY.md Appendix C generator, seed 2+rank)",
+            "frames_per_gpu": RATE * secs, "block_samples": 16384, "stereo_mode": "ms",
+            "l2": "inputs (345.6 MB PCM, ~213 MB payload per GPU) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"block-range sharding x{args.gpus}, NCCL all-gather of payload byte counts only"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seconds", type=int, default=600, help="audio seconds per GPU (configs[1] = 600)")
+    ap.add_argument("--cpu-seconds", type=int, default=60, help="audio seconds of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from __graft_entry__ import load_package
+    lacb = load_package()
+    cd = lacb.Codec(local_rank)  # raises if liblac_b200.so or the GPU is missing: no fallback
+
+    frames = RATE * args.seconds
+    pk = synth_packed(2 + rank, frames)
+    pcm_bytes = pk.size
+    nb = (frames + 16383) // 16384
+    sizes = np.full(nb, 16384, dtype=np.uint32)
+    sizes[-1] = frames - 16384 * (nb - 1)
+
+    d_pcm = cd.dev_malloc(pcm_bytes)
+    d_out = cd.dev_malloc(pcm_bytes)
+    cd.h2d(d_pcm, pk)
+    if dist:
+        counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        mine = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def barrier():
+        if dist:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    stats = {"enc_ms": 0.0, "dec_ms": 0.0, "analyze_ms": 0.0, "parse_ms": 0.0, "lac_bytes": 0, "enc_wall": 0.0,
+             "dec_wall": 0.0, "stages": {}}
+
+    def step_device(record):
+        t0 = time.perf_counter()
+        d_payload, nbytes, d_bb = cd.encode_device(d_pcm, 0, frames, DEPTH, CHANNELS, STEREO_MODE)
+        te = cd.timing()
+        bb = cd.d2h(d_bb, nb * 4, np.uint32)
+        if dist:  # global payload offsets = exclusive scan of the gathered byte counts (C1)
+            mine[0] = nbytes
+            dist.all_gather_into_tensor(counts, mine)
+            torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        cd.decode_device(d_payload, nbytes, sizes, bb, DEPTH, CHANNELS, STEREO_MODE, d_packed=d_out)
+        td = cd.timing()
+        t2 = time.perf_counter()
+        if record:
+            stats["enc_ms"] += te["total_ms"]
+            stats["dec_ms"] += td["total_ms"]
+            stats["analyze_ms"] += te["analyze_ms"]
+            stats["parse_ms"] += td["parse_ms"]
+            stats["enc_wall"] += t1 - t0
+            stats["dec_wall"] += t2 - t1
+            stats["lac_bytes"] = nbytes
+            for k, v in te.items():
+                stats["stages"]["enc_" + k] = stats["stages"].get("enc_" + k, 0.0) + v
+            for k, v in td.items():
+                if k in ("parse_ms", "finish_ms", "h2d_ms", "total_ms"):
+                    stats["stages"]["dec_" + k] = stats["stages"].get("dec_" + k, 0.0) + v
+        return nbytes, bb
+
+    for _ in range(args.warmup):
+        step_device(False)
+    # correctness of the very data being timed: round trip restores the PCM bit for bit
+    back = cd.d2h(d_out, pcm_bytes)
+    assert np.array_equal(back, pk), "device round trip does not restore the PCM"
+    del back
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device(True)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # end to end through the C ABI with host buffers (pinned input)
+    hp = C.c_void_p()
+    cd.lib.lacb_host_malloc(cd.h, pcm_bytes, C.byref(hp))
+    h_in = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint8)), shape=(pcm_bytes,))
+    h_in[:] = pk
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def step_host():
+        payload, bb, sz = cd.encode_blocks(None, None, DEPTH, STEREO_MODE, packed=h_in, channels=CHANNELS)
+        out, = cd.decode_blocks(payload, sz, bb, DEPTH, CHANNELS, STEREO_MODE, packed=True)
+        return payload.size, out
+
+    _, out = step_host()
+    assert np.array_equal(out, pk), "host round trip does not restore the PCM"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lac_e2e, _ = step_host()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    cd.lib.lacb_host_free(cd.h, hp)
+
+    if dist:
+        t = torch.tensor([wall, e2e_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, e2e_wall = float(t[0]), float(t[1])
+
+    if rank == 0:
+        K = args.steps
+        lac = stats["lac_bytes"]
+        value = pcm_bytes * world * K / wall / 1e9
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        analyze_s = stats["analyze_ms"] / K / 1e3
+        parse_s = stats["parse_ms"] / K / 1e3
+        achieved = (pcm_bytes + lac) / analyze_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": wall / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/int64 (u8 bitstream)", "data": "synthetic",
+            "config": workload_config(args, args.seconds),
+            "encode_gbs": pcm_bytes * world * K / stats["enc_wall"] / 1e9,
+            "decode_gbs": pcm_bytes * world * K / stats["dec_wall"] / 1e9,
+            "encode_gbs_device_events": pcm_bytes * K / (stats["enc_ms"] / 1e3) / 1e9,
+            "decode_gbs_device_events": pcm_bytes * K / (stats["dec_ms"] / 1e3) / 1e9,
+            "compression_ratio": lac / pcm_bytes,
+            "stage_ms_per_step": {k: round(v / K, 4) for k, v in sorted(stats["stages"].items())},
+            "roofline": {"bound": "hbm", "kernel": "k_analyze<1024,16> (encoder channel-block search)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_launch": pcm_bytes + lac},
+            "roofline_decode": {"bound": "hbm", "kernel": "k_decode_blocks (serial bitstream parse per block)",
+                                "achieved": (pcm_bytes + lac) / parse_s / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": (pcm_bytes + lac) / parse_s / 1e9 / peak},
+            "e2e": {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,
+                    "h2d_bytes_per_step": pcm_bytes + lac_e2e, "d2h_bytes_per_step": lac_e2e + pcm_bytes,
+                    "steps": e2e_steps},
+            "gpu_launches": K * 10,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            codec, kind = cpu_codec()
+            cores = os.cpu_count() or 1
+            secs = args.cpu_seconds
+            l, r = unpack24(pk[: RATE * secs * 6])
+            te, td, _ = cpu_roundtrip(codec, l, r, cores)
+            te2, td2, _ = cpu_roundtrip(codec, l, r, cores)
+            te, td = min(te, te2), min(td, td2)
+            sb = RATE * secs * 6
+            line["cpu_baseline"] = {"value": sb / (te + td) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "encode_gbs": sb / te / 1e9, "decode_gbs": sb / td / 1e9,
+                                    "sample": f"first {secs} s of the workload ({sb / 1e6:.1f} MB PCM), best of 2"}
+        print(json.dumps(line), flush=True)
+    cd.dev_free(d_pcm)
+    cd.dev_free(d_out)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

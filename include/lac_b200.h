@@ -95,12 +95,23 @@ int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const voi
                 uint64_t frames, uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes,
                 lacb_err* err);
 
-/* Same, with the int32 planes already resident on this context's device and the
- * results left there.  *d_payload and *d_block_bytes point into the context's
- * workspace and stay valid until the next call on the context. */
-int lacb_encode_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d_left, const int32_t* d_right,
+/* Same, with the PCM already resident on this context's device (d_a / d_b as pcm_a /
+ * pcm_b above, device pointers) and the results left there.  *d_payload and
+ * *d_block_bytes point into the context's workspace and stay valid until the next call
+ * on the context. */
+int lacb_encode_device(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* d_a, const void* d_b,
                        uint64_t frames, const uint8_t** d_payload, uint64_t* payload_bytes,
                        const uint32_t** d_block_bytes, lacb_err* err);
+
+/* Device / pinned-host memory helpers for callers that keep data resident on the GPU
+ * (all synchronous on the context's stream). */
+int lacb_dev_malloc(lacb_ctx* ctx, uint64_t bytes, void** out);
+int lacb_dev_free(lacb_ctx* ctx, void* p);
+int lacb_host_malloc(lacb_ctx* ctx, uint64_t bytes, void** out);
+int lacb_host_free(lacb_ctx* ctx, void* p);
+int lacb_memcpy_h2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int lacb_memcpy_d2h(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
+int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 
 /* Decode n_blocks blocks whose concatenated payloads start at `payload` (HOST memory).
  * block_sizes / block_bytes come from the v3 block table.  Output (HOST memory):

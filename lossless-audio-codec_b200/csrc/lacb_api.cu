@@ -316,28 +316,88 @@ int lacb_get_timing(const lacb_ctx* ctx, lacb_timing* out) {
   return 0;
 }
 
-int lacb_encode_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d_left, const int32_t* d_right,
+int lacb_encode_device(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* d_a, const void* d_b,
                        uint64_t frames, const uint8_t** d_payload, uint64_t* payload_bytes,
                        const uint32_t** d_block_bytes, lacb_err* err) {
   if (!ctx) return LACB_EINVAL;
-  if (!params_ok(prm) || !d_left || frames == 0 || (prm->channels == 2 && !d_right) ||
-      (frames + kMaxBlock - 1) / kMaxBlock > 0xFFFFFFu) {
+  if (!params_ok(prm) || !d_a || frames == 0 || (layout == LACB_PLANAR_I32 && prm->channels == 2 && !d_b) ||
+      (layout != LACB_PLANAR_I32 && layout != LACB_PACKED_LE) || (frames + kMaxBlock - 1) / kMaxBlock > 0xFFFFFFu) {
     ctx->err = "invalid encode arguments";
     set_err(err, LACB_EINVAL, 0, 0, "invalid encode arguments");
     return LACB_EINVAL;
   }
   CK(cudaSetDevice(ctx->device));
-  CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
-  CK(cudaEventRecord(ctx->ev[EV_H2D], ctx->stream));
+  cudaStream_t st = ctx->stream;
+  CK(cudaEventRecord(ctx->ev[EV_START], st));
+  CK(cudaEventRecord(ctx->ev[EV_H2D], st));
+  const int32_t* dL = static_cast<const int32_t*>(d_a);
+  const int32_t* dR = static_cast<const int32_t*>(d_b);
+  bool validate = prm->validate_range != 0;
+  if (layout == LACB_PACKED_LE) {
+    CKR(ensure(ctx, ctx->planeL, frames * 4));
+    if (prm->channels == 2) CKR(ensure(ctx, ctx->planeR, frames * 4));
+    const uint32_t grid = lacb_umin((uint32_t)((frames + 255) / 256), (uint32_t)ctx->sms * 16u);
+    auto kd = k_deinterleave;
+    LACB_LAUNCH(kd, grid ? grid : 1u, 256, 0, st, static_cast<const uint8_t*>(d_a), (u64)frames, prm->channels,
+                prm->bit_depth / 8u, as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR));
+    dL = as<int32_t>(ctx->planeL);
+    dR = as<int32_t>(ctx->planeR);
+    validate = false;
+  }
   uint64_t total = 0;
-  CKR(encode_on_device(ctx, prm, d_left, d_right, frames, prm->validate_range != 0, &total, err));
-  CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CKR(encode_on_device(ctx, prm, dL, dR, frames, validate, &total, err));
+  CK(cudaEventRecord(ctx->ev[EV_D2H], st));
+  CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   fill_enc_timing(ctx);
   if (d_payload) *d_payload = as<uint8_t>(ctx->payload);
   if (payload_bytes) *payload_bytes = total;
   if (d_block_bytes) *d_block_bytes = as<uint32_t>(ctx->blk_bytes);
+  return 0;
+}
+
+int lacb_dev_malloc(lacb_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMalloc(out, bytes ? bytes : 1));
+  return 0;
+}
+int lacb_dev_free(lacb_ctx* ctx, void* p) {
+  if (!ctx) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaFree(p));
+  return 0;
+}
+int lacb_host_malloc(lacb_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMallocHost(out, bytes ? bytes : 1));
+  return 0;
+}
+int lacb_host_free(lacb_ctx* ctx, void* p) {
+  if (!ctx) return LACB_EINVAL;
+  CK(cudaFreeHost(p));
+  return 0;
+}
+int lacb_memcpy_h2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int lacb_memcpy_d2h(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
@@ -555,12 +615,20 @@ int lacb_decode_device(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t*
                        const uint32_t* block_sizes_host, const uint32_t* block_bytes_host, uint32_t n_blocks,
                        int32_t* d_left, int32_t* d_right, uint8_t* d_packed, lacb_err* err) {
   if (!ctx) return LACB_EINVAL;
-  if (!dec_params_ok(prm) || !d_payload || !block_sizes_host || !block_bytes_host || n_blocks == 0 || !d_left ||
-      (prm->channels == 2 && !d_right)) {
+  if (!dec_params_ok(prm) || !d_payload || !block_sizes_host || !block_bytes_host || n_blocks == 0 ||
+      (d_left && prm->channels == 2 && !d_right)) {
     ctx->err = "invalid decode arguments";
     return LACB_EINVAL;
   }
   CK(cudaSetDevice(ctx->device));
+  if (!d_left) {  // planes are an intermediate: keep them in the context's workspace
+    u64 frames = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) frames += block_sizes_host[b];
+    CKR(ensure(ctx, ctx->d_L, frames * 4));
+    if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, frames * 4));
+    d_left = as<int32_t>(ctx->d_L);
+    d_right = as<int32_t>(ctx->d_R);
+  }
   CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
   CKR(decode_common(ctx, prm, d_payload, payload_bytes, block_sizes_host, block_bytes_host, n_blocks, d_left, d_right,
                     d_packed, err));

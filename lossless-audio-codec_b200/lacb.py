@@ -56,7 +56,8 @@ class BlockInfo(C.Structure):
 
 EXPORTS = ("lacb_create", "lacb_destroy", "lacb_last_error", "lacb_free", "lacb_device_count", "lacb_get_timing",
            "lacb_encode", "lacb_encode_device", "lacb_decode", "lacb_decode_device", "lacb_encode_block",
-           "lacb_decode_block", "lacb_lpc_analyze", "lacb_last_block_info")
+           "lacb_decode_block", "lacb_lpc_analyze", "lacb_last_block_info", "lacb_dev_malloc", "lacb_dev_free",
+           "lacb_host_malloc", "lacb_host_free", "lacb_memcpy_h2d", "lacb_memcpy_d2h", "lacb_memcpy_d2d")
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -80,7 +81,7 @@ def load_library(path=None) -> C.CDLL:
     lib.lacb_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     lib.lacb_encode.argtypes = [C.c_void_p, C.POINTER(EncParams), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                 C.POINTER(u8p), C.POINTER(C.c_uint64), u32p, C.POINTER(Err)]
-    lib.lacb_encode_device.argtypes = [C.c_void_p, C.POINTER(EncParams), C.c_void_p, C.c_void_p, C.c_uint64,
+    lib.lacb_encode_device.argtypes = [C.c_void_p, C.POINTER(EncParams), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                        C.POINTER(Err)]
     lib.lacb_decode.argtypes = [C.c_void_p, C.POINTER(DecParams), C.c_void_p, C.c_uint64, u32p, u32p, C.c_uint32,
@@ -92,6 +93,12 @@ def load_library(path=None) -> C.CDLL:
     lib.lacb_decode_block.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, i32p, C.POINTER(C.c_uint64)]
     lib.lacb_lpc_analyze.argtypes = [C.c_void_p, i32p, C.c_uint32, C.c_int, C.POINTER(C.c_int16)]
     lib.lacb_last_block_info.argtypes = [C.c_void_p, C.POINTER(BlockInfo)]
+    lib.lacb_dev_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lacb_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lacb_host_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+    lib.lacb_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    for fn in (lib.lacb_memcpy_h2d, lib.lacb_memcpy_d2h, lib.lacb_memcpy_d2d):
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     return lib
 
 
@@ -155,6 +162,60 @@ class Codec:
         t = Timing()
         self.lib.lacb_get_timing(self.h, C.byref(t))
         return {n: getattr(t, n) for n, _ in Timing._fields_}
+
+    # ---- device-resident path (inputs and outputs stay in HBM) -----------------------
+    def dev_malloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        if self.lib.lacb_dev_malloc(self.h, nbytes, C.byref(p)) != 0:
+            raise RuntimeError("lacb_dev_malloc: " + self.last_error())
+        return p.value
+
+    def dev_free(self, ptr: int):
+        self.lib.lacb_dev_free(self.h, C.c_void_p(ptr))
+
+    def h2d(self, dptr: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        if self.lib.lacb_memcpy_h2d(self.h, C.c_void_p(dptr), arr.ctypes.data, arr.nbytes) != 0:
+            raise RuntimeError("lacb_memcpy_h2d: " + self.last_error())
+
+    def d2h(self, dptr: int, nbytes: int, dtype=np.uint8) -> np.ndarray:
+        out = np.empty(nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        if self.lib.lacb_memcpy_d2h(self.h, out.ctypes.data, C.c_void_p(dptr), nbytes) != 0:
+            raise RuntimeError("lacb_memcpy_d2h: " + self.last_error())
+        return out
+
+    def d2d(self, dst: int, src: int, nbytes: int):
+        if self.lib.lacb_memcpy_d2d(self.h, C.c_void_p(dst), C.c_void_p(src), nbytes) != 0:
+            raise RuntimeError("lacb_memcpy_d2d: " + self.last_error())
+
+    def encode_device(self, d_a: int, d_b, frames: int, bit_depth, channels, stereo_mode, layout=LACB_PACKED_LE,
+                      zero_run=True, partitioning=True):
+        """PCM resident on the device -> (device payload pointer, payload bytes, device block-bytes pointer).
+        The returned pointers live in the context workspace until the next call."""
+        prm = EncParams(0, bit_depth, channels, stereo_mode, int(zero_run), int(partitioning), 0)
+        dp, n, dbb, err = C.c_void_p(), C.c_uint64(), C.c_void_p(), Err()
+        rc = self.lib.lacb_encode_device(self.h, C.byref(prm), layout, C.c_void_p(d_a),
+                                         C.c_void_p(d_b) if d_b else None, frames, C.byref(dp), C.byref(n),
+                                         C.byref(dbb), C.byref(err))
+        if rc != 0:
+            raise RuntimeError(f"lacb_encode_device rc={rc}: {self.last_error()}")
+        return dp.value, n.value, dbb.value
+
+    def decode_device(self, d_payload: int, payload_bytes: int, block_sizes, block_bytes, bit_depth, channels,
+                      stereo_mode, d_packed: int = 0, d_left: int = 0, d_right: int = 0):
+        bs = np.ascontiguousarray(block_sizes, dtype=np.uint32)
+        bb = np.ascontiguousarray(block_bytes, dtype=np.uint32)
+        prm = DecParams(bit_depth, channels, stereo_mode)
+        err = Err()
+        rc = self.lib.lacb_decode_device(self.h, C.byref(prm), C.c_void_p(d_payload), payload_bytes,
+                                         bs.ctypes.data_as(u32p), bb.ctypes.data_as(u32p), bs.size,
+                                         C.c_void_p(d_left) if d_left else None,
+                                         C.c_void_p(d_right) if d_right else None,
+                                         C.c_void_p(d_packed) if d_packed else None, C.byref(err))
+        if rc == LACB_EDECODE:
+            raise DecodeError(err.msg.decode())
+        if rc != 0:
+            raise RuntimeError(f"lacb_decode_device rc={rc}: {self.last_error()}")
 
     # ---- block payloads ------------------------------------------------------------
     def encode_blocks(self, left, right=None, bit_depth=16, stereo_mode=0, zero_run=True, partitioning=True,
