@@ -236,7 +236,7 @@ def main():
             for k, v in te.items():
                 stats["stages"]["enc_" + k] = stats["stages"].get("enc_" + k, 0.0) + v
             for k, v in td.items():
-                if k in ("parse_ms", "finish_ms", "h2d_ms", "total_ms"):
+                if k in ("parse_ms", "restore_ms", "finish_ms", "h2d_ms", "total_ms"):
                     stats["stages"]["dec_" + k] = stats["stages"].get("dec_" + k, 0.0) + v
         return nbytes, bb
 
@@ -313,7 +313,7 @@ def main():
                          "traffic": None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": pcm_bytes + lac},
-            "roofline_decode": {"bound": "hbm", "kernel": "k_decode_blocks (serial bitstream parse per block)",
+            "roofline_decode": {"bound": "hbm", "kernel": "k_parse_blocks (serial bitstream parse, one warp per block)",
                                 "achieved": (pcm_bytes + lac) / parse_s / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": (pcm_bytes + lac) / parse_s / 1e9 / peak},
             "e2e": {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,

@@ -73,7 +73,7 @@ typedef struct lacb_err {
 /* Per-stage device times of the last call on this context (CUDA events on its stream). */
 typedef struct lacb_timing {
   float h2d_ms, prep_ms, stereo_ms, lpc_ms, analyze_ms, finalize_ms, emit_ms, d2h_ms;
-  float parse_ms, finish_ms;
+  float parse_ms, restore_ms, finish_ms;
   float total_ms;
 } lacb_timing;
 
@@ -123,7 +123,9 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
                 void* out_a, void* out_b, lacb_err* err);
 
 /* Device-resident variant: payload and the two tables are device pointers, the planes
- * are written to d_left / d_right (device), optional packed output to d_packed. */
+ * are written to d_left / d_right (device; NULL = keep them in the context workspace),
+ * optional packed output to d_packed.  d_payload must be readable up to payload_bytes
+ * rounded up to a multiple of 16 (the bit reader loads aligned 32-bit words). */
 int lacb_decode_device(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* d_payload, uint64_t payload_bytes,
                        const uint32_t* block_sizes_host, const uint32_t* block_bytes_host, uint32_t n_blocks,
                        int32_t* d_left, int32_t* d_right, uint8_t* d_packed, lacb_err* err);

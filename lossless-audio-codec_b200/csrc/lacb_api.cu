@@ -37,7 +37,7 @@ struct lacb_ctx {
   cudaEvent_t ev[EV_COUNT] = {};
   DevBuf packed_in, planeL, planeR, flags, jobs, jobs_p, counts, acor, acor_p, lpcq, lpcq_p, recs, probe_bytes,
       blk_bytes, blk_off, misc, payload;
-  DevBuf d_payload, d_fs, d_size, d_boff, d_bytes, d_err, d_ms, d_L, d_R, d_packed;
+  DevBuf d_payload, d_fs, d_size, d_boff, d_bytes, d_err, d_ms, d_L, d_R, d_packed, d_hdrs;
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   lacb_block_info last_info{};
@@ -211,7 +211,7 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
   uint64_t tot;
   memcpy(&tot, hmisc + 2, 8);
   *total = tot;
-  CKR(ensure(ctx, ctx->payload, (size_t)tot + 8));
+  CKR(ensure(ctx, ctx->payload, (size_t)tot + 64));
   {
     auto ke = k_emit<FULL_NT, FULL_E>;
     LACB_LAUNCH(ke, lacb_umin(nb * cfg.channels, (uint32_t)ctx->sms), FULL_NT, kFullSmem, st, src, cfg,
@@ -240,13 +240,16 @@ bool params_ok(const lacb_enc_params* p) {
          p->stereo_mode <= 2;
 }
 
-__global__ void k_decode_one(const uint8_t* data, u64 size, uint32_t n, int32_t* out, u64* result) {
+__global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, uint32_t n, int32_t* out, u64* result) {
+  __shared__ uint32_t ring[kDriftWin];
+  __shared__ ChanHdr hdr;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  BitSrc s;
-  bs_init(s, data, data + size);
-  const bool ok = decode_channel_block(s, size * 8ull, n, out);
+  BitRd r;
+  rd_init(r, data, size, data + padded);
+  bool ok = parse_channel_block(r, n, out, &hdr, ring);
+  if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef);
   result[0] = ok ? 1ull : 0ull;
-  result[1] = ok ? s.consumed : 0ull;
+  result[1] = ok ? r.pos - r.start : 0ull;
 }
 
 }  // namespace
@@ -299,7 +302,7 @@ void lacb_destroy(lacb_ctx* ctx) {
                    &ctx->acor, &ctx->acor_p, &ctx->lpcq, &ctx->lpcq_p, &ctx->recs, &ctx->probe_bytes,
                    &ctx->blk_bytes, &ctx->blk_off, &ctx->misc, &ctx->payload, &ctx->d_payload, &ctx->d_fs,
                    &ctx->d_size, &ctx->d_boff, &ctx->d_bytes, &ctx->d_err, &ctx->d_ms, &ctx->d_L, &ctx->d_R,
-                   &ctx->d_packed};
+                   &ctx->d_packed, &ctx->d_hdrs};
   for (DevBuf* b : all) release(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < EV_COUNT; ++i)
@@ -562,10 +565,18 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   CK(cudaMemcpyAsync(ctx->d_bytes.p, h_bytes, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[EV_H2D], st));
   DecCfg cfg{prm->channels, prm->stereo_mode, prm->bit_depth, n_blocks};
-  auto kp = k_decode_blocks;
-  LACB_LAUNCH(kp, (n_blocks + 127u) / 128u, 128, 0, st, cfg, d_payload, as<u64>(ctx->d_fs), as<uint32_t>(ctx->d_size),
-              as<u64>(ctx->d_boff), as<uint32_t>(ctx->d_bytes), dL, dR, as<uint32_t>(ctx->d_err),
-              as<uint8_t>(ctx->d_ms));
+  CKR(ensure(ctx, ctx->d_hdrs, (size_t)n_blocks * 2 * sizeof(ChanHdr)));
+  auto kp = k_parse_blocks;
+  LACB_LAUNCH(kp, (n_blocks + kParseWarps - 1) / kParseWarps, 32 * kParseWarps, 0, st, cfg, d_payload,
+              (u64)((payload_bytes + 15ull) & ~15ull), as<u64>(ctx->d_fs), as<uint32_t>(ctx->d_size),
+              as<u64>(ctx->d_boff), as<uint32_t>(ctx->d_bytes), dL, dR, as<ChanHdr>(ctx->d_hdrs),
+              as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms));
+  CK(cudaEventRecord(ctx->ev[EV_LPC], st));
+  auto kr = k_restore_blocks;
+  LACB_LAUNCH(kr, (n_blocks * prm->channels + 63u) / 64u, 64, 0, st, cfg, as<u64>(ctx->d_fs),
+              as<uint32_t>(ctx->d_size), dL, dR, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err));
+  auto km = k_merge_restore_errors;
+  LACB_LAUNCH(km, (n_blocks + 255u) / 256u, 256, 0, st, cfg, as<uint32_t>(ctx->d_err));
   CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));
   auto kf = k_finish_pcm;
   LACB_LAUNCH(kf, lacb_umin(n_blocks, (uint32_t)ctx->sms * 8u), 256, 0, st, cfg, as<u64>(ctx->d_fs),
@@ -600,7 +611,8 @@ static void fill_dec_timing(lacb_ctx* ctx) {
   lacb_timing& t = ctx->timing;
   memset(&t, 0, sizeof t);
   t.h2d_ms = ev_ms(ctx, EV_START, EV_H2D);
-  t.parse_ms = ev_ms(ctx, EV_H2D, EV_ANALYZE);
+  t.parse_ms = ev_ms(ctx, EV_H2D, EV_LPC);
+  t.restore_ms = ev_ms(ctx, EV_LPC, EV_ANALYZE);
   t.finish_ms = ev_ms(ctx, EV_ANALYZE, EV_EMIT);
   t.d2h_ms = ev_ms(ctx, EV_EMIT, EV_D2H);
   t.total_ms = ev_ms(ctx, EV_START, EV_D2H);
@@ -660,7 +672,7 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
     frames += block_sizes[b];
   }
   const uint32_t bps = prm->bit_depth / 8;
-  CKR(ensure(ctx, ctx->d_payload, payload_bytes + 16));
+  CKR(ensure(ctx, ctx->d_payload, payload_bytes + 64));
   CKR(ensure(ctx, ctx->d_L, frames * 4));
   if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, frames * 4));
   if (layout == LACB_PACKED_LE) CKR(ensure(ctx, ctx->d_packed, frames * prm->channels * bps));
@@ -697,7 +709,8 @@ int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_
   if (size) CK(cudaMemcpyAsync(ctx->d_payload.p, data, size, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->d_L.p, 0, (size_t)block_size * 4, st));
   auto kd = k_decode_one;
-  LACB_LAUNCH(kd, 1, 32, 0, st, as<uint8_t>(ctx->d_payload), (u64)size, block_size, as<int32_t>(ctx->d_L),
+  LACB_LAUNCH(kd, 1, 32, 0, st, as<uint8_t>(ctx->d_payload), (u64)size, (u64)((size + 15ull) & ~15ull), block_size,
+              as<int32_t>(ctx->d_L),
               as<u64>(ctx->misc));
   u64 res[2] = {0, 0};
   CK(cudaMemcpyAsync(res, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));

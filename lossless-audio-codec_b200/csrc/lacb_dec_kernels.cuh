@@ -3,14 +3,19 @@
 // The .lac block bitstream is inherently serial inside a block: variable-length
 // codes whose Rice parameter adapts to every decoded value, and no byte offsets for
 // partitions or for the second channel (docs/format.md:18-27).  The
-// parallelism is the block count, so the parser runs one thread per frame-block
-// (32 independent streams per warp, each lane with its own 64-bit bit window), and
-// everything that is data parallel (mid/side reconstruction, PCM range validation,
-// interleave + 16/24-bit packing) is a separate bandwidth-bound kernel.
-//   Block::Decoder::decode_into   src/codec/block/decoder.cpp:64-520
-//   LAC::Decoder decode_block     src/codec/lac/decoder.cpp:167-207
-//   reconstruct_mid_side_in_place src/codec/lac/decoder.cpp:48-65
-//   pack_pcm_to_wav_bytes         src/main.cpp:150-182
+// only parallelism the format offers is the block count, so:
+//   k_parse_blocks   one warp per frame-block; lane 0 walks the bitstream with a
+//                    64-bit peek window (3 cached word loads + 2 funnel shifts per
+//                    symbol, no refill state), the closed-form division-free k model
+//                    and a 256-entry shared-memory ring for the drift window.  A
+//                    divergent thread-per-block layout was measured 40x slower.
+//   k_restore_blocks one thread per channel-block: fixed / FIR / LPC reconstruction,
+//                    counted loops without data-dependent trip counts.
+//   k_finish_pcm     mid/side reconstruction, PCM range validation, interleave +
+//                    16/24-bit packing; fully data parallel and bandwidth bound.
+// Reference: Block::Decoder::decode_into src/codec/block/decoder.cpp:64-520,
+// LAC::Decoder decode_block src/codec/lac/decoder.cpp:167-207,
+// reconstruct_mid_side_in_place :48-65, pack_pcm_to_wav_bytes src/main.cpp:150-182.
 #pragma once
 #include "lacb_common.cuh"
 
@@ -25,83 +30,92 @@ enum : uint32_t {
   DERR_TRAILING = 5,   // "block=<i> channel=trailing-payload"
 };
 
-// MSB-first bit reader over [p, end); reads past the end deliver zeros and are
-// detected through the consumed-bit count (BitReader, bitstream/bit_reader.hpp:40-202).
-struct BitSrc {
-  const uint8_t* p;    // next byte to load
-  const uint8_t* end;
-  u64 w;               // window, next bit at bit 63
-  int avail;           // valid bits in w
-  u64 consumed;        // bits handed out so far
+// MSB-first bit reader (BitReader, bitstream/bit_reader.hpp:40-202).  `base` is the
+// 4-byte aligned address at or before the first byte; positions are bit offsets from it.
+// Reads past `end` return whatever follows (clamped to the last readable word) and are
+// caught by the pos > end checks, which is how the reference's "ran out of data" errors
+// are reproduced.
+struct BitRd {
+  const uint32_t* base;
+  u64 pos, start, end;
+  uint32_t last_word;
 };
-__device__ __forceinline__ void bs_init(BitSrc& s, const uint8_t* p, const uint8_t* end) {
-  s.p = p;
-  s.end = end;
-  s.w = 0ull;
-  s.avail = 0;
-  s.consumed = 0ull;
+__device__ __forceinline__ void rd_init(BitRd& r, const uint8_t* begin, u64 nbytes, const uint8_t* buf_end) {
+  const uint64_t a = reinterpret_cast<uint64_t>(begin);
+  r.base = reinterpret_cast<const uint32_t*>(a & ~(uint64_t)3);
+  r.start = (a & 3ull) * 8ull;
+  r.pos = r.start;
+  r.end = r.start + nbytes * 8ull;
+  // last word that lies entirely inside the caller's buffer
+  const uint64_t lastb = reinterpret_cast<uint64_t>(buf_end);
+  const uint64_t words = (lastb - (a & ~(uint64_t)3)) >> 2;
+  r.last_word = words ? (uint32_t)(words - 1ull > 0xFFFFFFFEull ? 0xFFFFFFFEull : words - 1ull) : 0u;
 }
-__device__ __forceinline__ void bs_refill(BitSrc& s) {
-  while (s.avail <= 56) {
-    const u64 byte = (s.p < s.end) ? (u64)(*s.p) : 0ull;
-    s.p++;
-    s.w |= byte << (56 - s.avail);
-    s.avail += 8;
-  }
+__device__ __forceinline__ uint32_t rd_word(const BitRd& r, u64 wi) {
+  const uint32_t i = wi > (u64)r.last_word ? r.last_word : (uint32_t)wi;
+  return __byte_perm(__ldg(r.base + i), 0u, 0x0123);
+}
+// the next 64 bits
+__device__ __forceinline__ u64 rd_peek(const BitRd& r) {
+  const u64 wi = r.pos >> 5;
+  const uint32_t sh = (uint32_t)r.pos & 31u;
+  const uint32_t w0 = rd_word(r, wi), w1 = rd_word(r, wi + 1ull), w2 = rd_word(r, wi + 2ull);
+  const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
+  return ((u64)hi << 32) | lo;
 }
 // n in [0,32]
-__device__ __forceinline__ uint32_t bs_get(BitSrc& s, uint32_t n) {
+__device__ __forceinline__ uint32_t rd_get(BitRd& r, uint32_t n) {
   if (n == 0u) return 0u;
-  if (s.avail < (int)n) bs_refill(s);
-  const uint32_t v = (uint32_t)(s.w >> (64u - n));
-  s.w <<= n;
-  s.avail -= (int)n;
-  s.consumed += n;
-  return v;
+  const u64 w = rd_peek(r);
+  r.pos += n;
+  return (uint32_t)(w >> (64u - n));
 }
-__device__ __forceinline__ u64 bs_size_bits(const BitSrc& s, const uint8_t* begin) { return (u64)(s.end - begin) * 8ull; }
-// unary: count ones up to the 0 terminator; fails if more than max_ones or the data ends
-__device__ __forceinline__ bool bs_unary(BitSrc& s, uint32_t max_ones, u64 limit_bits, uint32_t* ones) {
-  uint32_t q = 0u;
+__device__ __forceinline__ bool rd_over(const BitRd& r) { return r.pos > r.end; }
+
+// read_rice_unsigned (block/decoder.cpp:74-83): unary quotient limited to
+// UINT32_MAX >> k ones (read_unary_ones, bit_reader.hpp:140-172), then k remainder bits.
+__device__ __forceinline__ bool rd_rice(BitRd& r, uint32_t k, uint32_t* value) {
+  const u64 w = rd_peek(r);
+  const uint32_t hi = (uint32_t)(w >> 32);
+  uint32_t q;
+  if (hi != 0xFFFFFFFFu) {  // fast path: terminator within 32 bits, q + 1 + k <= 63
+    q = (uint32_t)__clz((int)~hi);
+    const uint32_t rem = k ? (uint32_t)((w << (q + 1u)) >> (64u - k)) : 0u;
+    r.pos += q + 1u + k;
+    if (q > (0xFFFFFFFFu >> k) || r.pos > r.end) return false;
+    *value = (q << k) | rem;
+    return true;
+  }
+  // long unary run: walk word by word
+  const uint32_t max_ones = 0xFFFFFFFFu >> k;
+  q = 0u;
   for (;;) {
-    if (s.avail < 32) bs_refill(s);
-    const uint32_t top = (uint32_t)(s.w >> 32);
-    const uint32_t run = (uint32_t)__clz((int)~top);  // leading ones among the top 32 bits
+    const uint32_t top = (uint32_t)(rd_peek(r) >> 32);
+    const uint32_t run = (uint32_t)__clz((int)~top);
     if (run < 32u) {
       q += run;
-      s.w <<= (run + 1u);
-      s.avail -= (int)(run + 1u);
-      s.consumed += run + 1u;
+      r.pos += run + 1u;
       break;
     }
     q += 32u;
-    s.w <<= 32;
-    s.avail -= 32;
-    s.consumed += 32u;
-    if (s.consumed > limit_bits || q > max_ones) return false;
+    r.pos += 32u;
+    if (r.pos > r.end || q > max_ones) return false;
   }
-  *ones = q;
-  return q <= max_ones && s.consumed <= limit_bits;
-}
-__device__ __forceinline__ bool bs_rice(BitSrc& s, uint32_t k, u64 limit_bits, uint32_t* value) {
-  // read_rice_unsigned, block/decoder.cpp:74-83
-  if (k > 31u) return false;
-  uint32_t q;
-  if (!bs_unary(s, 0xFFFFFFFFu >> k, limit_bits, &q)) return false;
-  const uint32_t rem = bs_get(s, k);
-  if (s.consumed > limit_bits) return false;
+  if (q > max_ones || r.pos > r.end) return false;
+  const uint32_t rem = rd_get(r, k);
+  if (r.pos > r.end) return false;
   *value = (q << k) | rem;
   return true;
 }
 
-// Incremental adaptive-k state (rice.hpp:15-114) kept in registers.  The 256-entry
-// ring of recent values is the already decoded residual array itself.
+// Incremental adaptive-k state (rice.hpp:15-114).  ring[] is the 256-entry window of
+// recent zig-zag values (shared memory, one per warp).
 struct KState {
   u64 sum, win_sum;
   uint32_t count;
   uint32_t lg[3], zr[3];  // 96-bit shift registers of the large / zero flags (bit 0 = newest)
   uint32_t large_cnt, zero_cnt;
-  uint32_t kb;            // previous base k (hint)
+  uint32_t kb;            // previous base k (search hint)
 };
 __device__ __forceinline__ void ks_reset(KState& st) {
   st.sum = st.win_sum = 0ull;
@@ -111,19 +125,18 @@ __device__ __forceinline__ void ks_reset(KState& st) {
   st.large_cnt = st.zero_cnt = 0u;
   st.kb = 1u;
 }
-// advance the model by one sample with zig-zag value u; `old_u` is the value that
-// leaves the 256-sample drift window (ignored while count <= 256)
 template <bool STATELESS>
-__device__ __forceinline__ uint32_t ks_step(KState& st, uint32_t u, uint32_t old_u) {
+__device__ __forceinline__ uint32_t ks_step(KState& st, uint32_t u, uint32_t* ring) {
   st.sum += u;
-  st.count++;
-  const uint32_t c = st.count;
+  const uint32_t c = ++st.count;
   const u64 N = st.sum + (c >> 1);
   const uint32_t kb = kbase_from(N, c, st.kb);
   st.kb = kb ? kb : 1u;
   if (STATELESS) return kb;
+  const uint32_t slot = (c - 1u) & (kDriftWin - 1u);
   st.win_sum += u;
-  if (c > kDriftWin) st.win_sum -= old_u;
+  if (c > kDriftWin) st.win_sum -= ring[slot];
+  ring[slot] = u;
   const uint32_t q = (kb >= 31u) ? 0u : (u >> kb);
   const uint32_t is_l = q > 3u, is_z = q == 0u;
   st.large_cnt += is_l - (st.lg[2] >> 31);
@@ -148,18 +161,19 @@ __device__ __forceinline__ uint32_t ks_step(KState& st, uint32_t u, uint32_t old
     if (st.large_cnt * 4u >= 288u) bias = bias + 1 < 1 ? bias + 1 : 1;
     else if (st.zero_cnt * 5u >= 384u) bias = bias - 1 > -1 ? bias - 1 : -1;
   }
-  int k = (int)kb + bias;
+  const int k = (int)kb + bias;
   return (uint32_t)(k < 0 ? 0 : (k > 31 ? 31 : k));
 }
 
 // decode_residual_segment, block/decoder.cpp:104-306.  `res` points at the segment.
 template <bool STATELESS>
-__device__ __forceinline__ bool decode_segment(BitSrc& s, u64 limit, uint32_t n, uint32_t k0, uint32_t mode,
-                                               int32_t* res) {
+__device__ __forceinline__ bool decode_segment(BitRd& r, uint32_t n, uint32_t k0, uint32_t mode, int32_t* res,
+                                               uint32_t* ring) {
   if (mode == MODE_STATIC) {
+    if (k0 > 31u) return false;
     for (uint32_t i = 0; i < n; ++i) {
       uint32_t u;
-      if (!bs_rice(s, k0, limit, &u)) return false;
+      if (!rd_rice(r, k0, &u)) return false;
       res[i] = unzz32(u);
     }
     return true;
@@ -168,52 +182,133 @@ __device__ __forceinline__ bool decode_segment(BitSrc& s, u64 limit, uint32_t n,
   ks_reset(st);
   uint32_t k = k0;
   uint32_t idx = 0u;
-  while (idx < n) {
-    uint32_t u = 0u;
-    uint32_t run = 0u;  // > 0: a zero run of that length was decoded instead of one value
-    if (mode == MODE_RICE) {
-      if (!bs_rice(s, k, limit, &u)) return false;
-    } else if (mode == MODE_BIN) {
-      const uint32_t tag = bs_get(s, 2u);
-      if (s.consumed > limit) return false;
-      if (tag == 0u) {
-        u = 0u;
-      } else if (tag == 3u) {
-        if (!bs_rice(s, k, limit, &u)) return false;
-      } else {
-        const uint32_t sign = bs_get(s, 1u);
-        if (s.consumed > limit) return false;
+  if (mode == MODE_RICE) {
+    while (idx < n) {
+      uint32_t u;
+      if (!rd_rice(r, k, &u)) return false;
+      res[idx++] = unzz32(u);
+      k = ks_step<STATELESS>(st, u, ring);
+    }
+    return true;
+  }
+  if (mode == MODE_BIN) {
+    while (idx < n) {
+      const uint32_t tag = rd_get(r, 2u);
+      if (rd_over(r)) return false;
+      uint32_t u = 0u;
+      if (tag == 3u) {
+        if (!rd_rice(r, k, &u)) return false;
+      } else if (tag != 0u) {
+        const uint32_t sign = rd_get(r, 1u);
+        if (rd_over(r)) return false;
         u = (tag == 1u) ? (sign ? 1u : 2u) : (sign ? 3u : 4u);
       }
-    } else {  // MODE_ZR
-      const uint32_t tag = bs_get(s, 2u);
-      if (s.consumed > limit) return false;
-      if (tag > 2u) return false;
-      if (tag == 0u) {
-        if (!bs_rice(s, k, limit, &u)) return false;
-      } else if (tag == 2u) {
-        u = bs_get(s, 32u);
-        if (s.consumed > limit) return false;
-      } else {
-        uint32_t enc;
-        if (!bs_rice(s, kZrRunK, limit, &enc) || enc > 0xFFFFFFFFu - kZrMinRun) return false;
-        run = enc + kZrMinRun;
-        if (run > n - idx) return false;
-      }
+      res[idx++] = unzz32(u);
+      k = ks_step<STATELESS>(st, u, ring);
     }
-    if (run) {
+    return true;
+  }
+  // MODE_ZR
+  while (idx < n) {
+    const uint32_t tag = rd_get(r, 2u);
+    if (rd_over(r)) return false;
+    if (tag > 2u) return false;
+    if (tag == 1u) {
+      uint32_t enc;
+      if (!rd_rice(r, kZrRunK, &enc) || enc > 0xFFFFFFFFu - kZrMinRun) return false;
+      const uint32_t run = enc + kZrMinRun;
+      if (run > n - idx) return false;
       for (uint32_t j = 0; j < run; ++j) {
-        res[idx] = 0;
-        const uint32_t old_u = (!STATELESS && idx >= kDriftWin) ? zz32(res[idx - kDriftWin]) : 0u;
-        k = ks_step<STATELESS>(st, 0u, old_u);
-        ++idx;
+        res[idx++] = 0;
+        k = ks_step<STATELESS>(st, 0u, ring);
       }
-    } else {
-      res[idx] = unzz32(u);
-      const uint32_t old_u = (!STATELESS && idx >= kDriftWin) ? zz32(res[idx - kDriftWin]) : 0u;
-      k = ks_step<STATELESS>(st, u, old_u);
-      ++idx;
+      continue;
     }
+    uint32_t u;
+    if (tag == 0u) {
+      if (!rd_rice(r, k, &u)) return false;
+    } else {
+      u = rd_get(r, 32u);
+      if (rd_over(r)) return false;
+    }
+    res[idx++] = unzz32(u);
+    k = ks_step<STATELESS>(st, u, ring);
+  }
+  return true;
+}
+
+__device__ __forceinline__ uint32_t part_len(uint32_t n, uint32_t p, uint32_t idx) {
+  if (p == 0u) return n;
+  const uint32_t base = n >> p, cnt = 1u << p;
+  return (idx + 1u == cnt) ? n - base * (cnt - 1u) : base;
+}
+
+// What the restore stage needs to know about a parsed channel-block.
+struct ChanHdr {
+  uint8_t type, order;
+  int16_t coef[33];
+};
+
+// Header + residual part of Block::Decoder::decode_into (block/decoder.cpp:64-512):
+// leaves the residual in `out` and the predictor description in `hdr`.
+__device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_t* out, ChanHdr* hdr, uint32_t* ring) {
+  if (n == 0u || n > kMaxBlock) return false;
+  const uint32_t type = rd_get(r, 8u);
+  const uint32_t order = rd_get(r, 8u);
+  if (rd_over(r)) return false;
+  if (type > 2u) return false;
+  if (type == PRED_LPC) {
+    if (order == 0u || order > 32u || order >= n) return false;
+  } else if (type == PRED_FIR) {
+    if (order != 2u) return false;
+  } else if (order > 4u) {
+    return false;
+  }
+  hdr->type = (uint8_t)type;
+  hdr->order = (uint8_t)order;
+  if (type == PRED_LPC) {
+    for (uint32_t i = 1; i <= order; ++i) {
+      hdr->coef[i] = (int16_t)(uint16_t)rd_get(r, 16u);
+      if (rd_over(r)) return false;
+    }
+  }
+  const uint32_t control = rd_get(r, 8u);
+  if (rd_over(r)) return false;
+  if (control & 0x10u) return false;
+  const bool pflag = (control & 0x80u) != 0u;
+  const uint32_t p = control & 0x0Fu, cmode = (control >> 5) & 3u;
+  if (pflag && p == 0u) return false;
+  if (!pflag && p != 0u) return false;
+  if (p > kMaxPartOrder) return false;
+  if (p > 0u && (n >> p) < kMinPart) return false;
+  const uint32_t cnt = 1u << p;
+  // the partition table sits in front of the tokens (block/decoder.cpp:447-455): remember
+  // where it starts and read each entry when its segment comes up
+  const u64 table_pos = r.pos;
+  r.pos += 7ull * cnt;
+  if (rd_over(r)) return false;
+  const u64 tokens_pos = r.pos;
+  r.pos = table_pos;
+  const uint32_t first = rd_get(r, 7u);
+  if ((first >> 5) != cmode) return false;
+  r.pos = tokens_pos;
+  uint32_t off = 0u;
+  for (uint32_t i = 0; i < cnt; ++i) {
+    const u64 save = r.pos;
+    r.pos = table_pos + 7ull * i;
+    const uint32_t mk = rd_get(r, 7u);
+    r.pos = save;
+    const uint32_t len = part_len(n, p, i);
+    const bool ok = p ? decode_segment<true>(r, len, mk & 31u, mk >> 5, out + off, ring)
+                      : decode_segment<false>(r, len, mk & 31u, mk >> 5, out + off, ring);
+    if (!ok) return false;
+    off += len;
+  }
+  // consume_zero_padding_to_byte (bit_reader.hpp:180-185)
+  const uint32_t padn = (uint32_t)((8ull - ((r.pos - r.start) & 7ull)) & 7ull);
+  if (padn) {
+    if (rd_get(r, padn) != 0u) return false;
+    if (rd_over(r)) return false;
   }
   return true;
 }
@@ -284,104 +379,72 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
   return true;
 }
 
-__device__ __forceinline__ uint32_t part_len(uint32_t n, uint32_t p, uint32_t idx) {
-  if (p == 0u) return n;
-  const uint32_t base = n >> p, cnt = 1u << p;
-  return (idx + 1u == cnt) ? n - base * (cnt - 1u) : base;
-}
-
-// Block::Decoder::decode_into (block/decoder.cpp:64-520)
-__device__ __forceinline__ bool decode_channel_block(BitSrc& s, u64 limit, uint32_t n, int32_t* out) {
-  if (n == 0u || n > kMaxBlock) return false;
-  const uint32_t type = bs_get(s, 8u);
-  const uint32_t order = bs_get(s, 8u);
-  if (s.consumed > limit) return false;
-  if (type > 2u) return false;
-  if (type == PRED_LPC) {
-    if (order == 0u || order > 32u || order >= n) return false;
-  } else if (type == PRED_FIR) {
-    if (order != 2u) return false;
-  } else if (order > 4u) {
-    return false;
-  }
-  int16_t c[33];
-  for (int i = 0; i < 33; ++i) c[i] = 0;
-  if (type == PRED_LPC) {
-    for (uint32_t i = 1; i <= order; ++i) {
-      c[i] = (int16_t)(uint16_t)bs_get(s, 16u);
-      if (s.consumed > limit) return false;
-    }
-  }
-  const uint32_t control = bs_get(s, 8u);
-  if (s.consumed > limit) return false;
-  if (control & 0x10u) return false;
-  const bool pflag = (control & 0x80u) != 0u;
-  const uint32_t p = control & 0x0Fu, cmode = (control >> 5) & 3u;
-  if (pflag && p == 0u) return false;
-  if (!pflag && p != 0u) return false;
-  if (p > kMaxPartOrder) return false;
-  if (p > 0u && (n >> p) < kMinPart) return false;
-  const uint32_t cnt = 1u << p;
-  // partition metadata is read up front (block/decoder.cpp:447-455), then the segments
-  uint8_t mk[256];
-  for (uint32_t i = 0; i < cnt; ++i) {
-    const uint32_t m = bs_get(s, 2u);
-    const uint32_t k = bs_get(s, 5u);
-    if (s.consumed > limit) return false;
-    mk[i] = (uint8_t)((m << 5) | k);
-  }
-  if ((uint32_t)(mk[0] >> 5) != cmode) return false;
-  uint32_t off = 0u;
-  for (uint32_t i = 0; i < cnt; ++i) {
-    const uint32_t len = part_len(n, p, i);
-    const uint32_t m = mk[i] >> 5, k = mk[i] & 31u;
-    const bool ok = p ? decode_segment<true>(s, limit, len, k, m, out + off)
-                      : decode_segment<false>(s, limit, len, k, m, out + off);
-    if (!ok) return false;
-    off += len;
-  }
-  // consume_zero_padding_to_byte (bit_reader.hpp:180-185)
-  const uint32_t padn = (uint32_t)((8u - (s.consumed & 7ull)) & 7ull);
-  if (padn) {
-    if (bs_get(s, padn) != 0u) return false;
-    if (s.consumed > limit) return false;
-  }
-  return restore_block(out, n, type, order, c);
-}
-
 struct DecCfg {
   uint32_t channels, stereo_mode, bit_depth, n_blocks;
 };
 
-// K12: one thread per frame-block.  blk_fs[b] = first sample of block b, blk_size[b] its
-// sample count, blk_boff[b] its byte offset inside `payload`, blk_bytes[b] its byte size.
-__global__ void __launch_bounds__(128) k_decode_blocks(DecCfg cfg, const uint8_t* __restrict__ payload,
-                                                       const u64* __restrict__ blk_fs,
-                                                       const uint32_t* __restrict__ blk_size,
-                                                       const u64* __restrict__ blk_boff,
-                                                       const uint32_t* __restrict__ blk_bytes, int32_t* L, int32_t* R,
-                                                       uint32_t* blk_err, uint8_t* blk_ms) {
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= cfg.n_blocks) return;
+// K12a: one warp per frame-block, lane 0 parses.  blk_fs[b] = first sample of block b,
+// blk_size[b] its sample count, blk_boff[b] its byte offset inside `payload`,
+// blk_bytes[b] its byte size.  Residuals go to the planes, predictor headers to hdrs[2b+ch].
+constexpr int kParseWarps = 2;
+__global__ void __launch_bounds__(32 * kParseWarps) k_parse_blocks(
+    DecCfg cfg, const uint8_t* __restrict__ payload, u64 payload_bytes, const u64* __restrict__ blk_fs,
+    const uint32_t* __restrict__ blk_size, const u64* __restrict__ blk_boff, const uint32_t* __restrict__ blk_bytes,
+    int32_t* L, int32_t* R, ChanHdr* hdrs, uint32_t* blk_err, uint8_t* blk_ms) {
+  __shared__ uint32_t rings[kParseWarps][kDriftWin];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t b = blockIdx.x * kParseWarps + warp;
+  if (b >= cfg.n_blocks || lane != 0u) return;
+  uint32_t* ring = rings[warp];
   const uint8_t* begin = payload + blk_boff[b];
-  BitSrc s;
-  bs_init(s, begin, begin + blk_bytes[b]);
-  const u64 limit = (u64)blk_bytes[b] * 8ull;
+  BitRd r;
+  rd_init(r, begin, blk_bytes[b], payload + payload_bytes);
   const uint32_t n = blk_size[b];
   uint32_t err = DERR_OK;
   uint32_t ms = 0u;
   if (cfg.channels == 2u && cfg.stereo_mode == 2u) {
-    const uint32_t flag = bs_get(s, 8u);
-    if (s.consumed > limit || flag > 1u) err = DERR_FLAG;
+    const uint32_t flag = rd_get(r, 8u);
+    if (rd_over(r) || flag > 1u) err = DERR_FLAG;
     ms = flag == 1u;
   } else if (cfg.channels == 2u && cfg.stereo_mode == 1u) {
     ms = 1u;
   }
-  if (!err && !decode_channel_block(s, limit, n, L + blk_fs[b])) err = DERR_PRIMARY;
-  if (!err && cfg.channels == 2u && !decode_channel_block(s, limit, n, R + blk_fs[b])) err = DERR_SECONDARY;
-  if (!err && s.consumed != limit) err = DERR_TRAILING;
+  if (!err && !parse_channel_block(r, n, L + blk_fs[b], hdrs + (size_t)b * 2u, ring)) err = DERR_PRIMARY;
+  if (!err && cfg.channels == 2u && !parse_channel_block(r, n, R + blk_fs[b], hdrs + (size_t)b * 2u + 1u, ring))
+    err = DERR_SECONDARY;
+  if (!err && r.pos != r.end) err = DERR_TRAILING;  // checked after reconstruction in the reference
   blk_err[b] = err;
   blk_ms[b] = (uint8_t)ms;
+}
+
+// K12b: one thread per channel-block.  A reconstruction overflow is a primary / secondary
+// channel failure (Block::Decoder::decode_into returns false), which outranks the
+// trailing-payload error recorded by the parser.
+__global__ void __launch_bounds__(64) k_restore_blocks(DecCfg cfg, const u64* __restrict__ blk_fs,
+                                                       const uint32_t* __restrict__ blk_size, int32_t* L, int32_t* R,
+                                                       const ChanHdr* __restrict__ hdrs, uint32_t* blk_err) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cfg.n_blocks * cfg.channels) return;
+  const uint32_t b = j / cfg.channels, ch = j - b * cfg.channels;
+  const uint32_t e = blk_err[b] & 0xFFu;
+  if (e == DERR_FLAG || e == DERR_PRIMARY || (e == DERR_SECONDARY && ch == 1u)) return;
+  const ChanHdr* h = hdrs + (size_t)b * 2u + ch;
+  int32_t* x = (ch ? R : L) + blk_fs[b];
+  if (!restore_block(x, blk_size[b], h->type, h->order, h->coef)) atomicOr(&blk_err[b], 0x100u << ch);
+}
+// Folds the restore verdicts (bits 8/9) into the per-block code in the reference's order:
+// primary parse, primary reconstruction, secondary parse, secondary reconstruction.
+__global__ void k_merge_restore_errors(DecCfg cfg, uint32_t* blk_err) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= cfg.n_blocks) return;
+  const uint32_t v = blk_err[b];
+  if (!(v & 0x300u)) return;
+  uint32_t e = v & 0xFFu;
+  if (e != DERR_FLAG && e != DERR_PRIMARY) {
+    if (v & 0x100u) e = DERR_PRIMARY;
+    else if (e != DERR_SECONDARY && (v & 0x200u)) e = DERR_SECONDARY;
+  }
+  blk_err[b] = e;
 }
 
 // M/S reconstruction + depth validation + optional interleaved packing; one CTA per block.

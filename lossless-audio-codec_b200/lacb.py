@@ -44,7 +44,7 @@ class Err(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("h2d_ms", "prep_ms", "stereo_ms", "lpc_ms", "analyze_ms", "finalize_ms",
-                                         "emit_ms", "d2h_ms", "parse_ms", "finish_ms", "total_ms")]
+                                         "emit_ms", "d2h_ms", "parse_ms", "restore_ms", "finish_ms", "total_ms")]
 
 
 class BlockInfo(C.Structure):
