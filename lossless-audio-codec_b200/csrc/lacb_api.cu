@@ -249,7 +249,7 @@ __global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, uint32_t
   bool ok = parse_channel_block(r, n, out, &hdr, ring);
   if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef);
   result[0] = ok ? 1ull : 0ull;
-  result[1] = ok ? r.pos - r.start : 0ull;
+  result[1] = ok ? rd_pos(r) - r.start : 0ull;
 }
 
 }  // namespace

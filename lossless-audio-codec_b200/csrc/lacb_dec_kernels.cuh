@@ -30,82 +30,104 @@ enum : uint32_t {
   DERR_TRAILING = 5,   // "block=<i> channel=trailing-payload"
 };
 
-// MSB-first bit reader (BitReader, bitstream/bit_reader.hpp:40-202).  `base` is the
-// 4-byte aligned address at or before the first byte; positions are bit offsets from it.
-// Reads past `end` return whatever follows (clamped to the last readable word) and are
-// caught by the pos > end checks, which is how the reference's "ran out of data" errors
-// are reproduced.
+// MSB-first bit reader (BitReader, bitstream/bit_reader.hpp:40-202), register resident:
+// a 64-bit window `w` (next bit at bit 63, `avail` valid bits) plus the following
+// big-endian word already loaded (`nextw`), so a refill is a shift/or and the cached load
+// it triggers is for data needed 32+ bits later (off the dependent chain).  After
+// rd_refill() at least 33 bits are valid, enough for a unary prefix of <= 31 ones with its
+// terminator, or for any fixed field (<= 32 bits).  `base` is the 4-byte aligned address at
+// or before the first byte; positions are bit offsets from it.  Reads past `end` return
+// whatever follows (word index clamped to the caller's buffer) and are caught by the
+// rd_over() checks at segment granularity, which is how the reference's "ran out of data"
+// rejections are reproduced.
 struct BitRd {
   const uint32_t* base;
-  u64 pos, start, end;
+  u64 w;
+  uint32_t avail;   // valid bits in w
+  uint32_t wi;      // index of the word held in nextw
+  uint32_t nextw;
   uint32_t last_word;
+  u64 start, end;
 };
+__device__ __forceinline__ uint32_t rd_word(const BitRd& r, uint32_t i) {
+  i = i > r.last_word ? r.last_word : i;
+  return __byte_perm(__ldg(r.base + i), 0u, 0x0123);
+}
+__device__ __forceinline__ u64 rd_pos(const BitRd& r) { return (u64)r.wi * 32ull - r.avail; }
+__device__ __forceinline__ void rd_refill(BitRd& r) {
+  if (r.avail <= 32u) {
+    r.w |= (u64)r.nextw << (32u - r.avail);
+    r.avail += 32u;
+    r.wi += 1u;
+    r.nextw = rd_word(r, r.wi);
+  }
+}
+__device__ __forceinline__ void rd_seek(BitRd& r, u64 pos) {
+  const u64 wq = pos >> 5;
+  const uint32_t w0 = wq > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)wq;
+  const uint32_t sh = (uint32_t)pos & 31u;
+  r.w = (u64)rd_word(r, w0) << (32u + sh);
+  r.avail = 32u - sh;
+  r.wi = w0 + 1u;
+  r.nextw = rd_word(r, r.wi);
+  rd_refill(r);
+}
 __device__ __forceinline__ void rd_init(BitRd& r, const uint8_t* begin, u64 nbytes, const uint8_t* buf_end) {
   const uint64_t a = reinterpret_cast<uint64_t>(begin);
   r.base = reinterpret_cast<const uint32_t*>(a & ~(uint64_t)3);
   r.start = (a & 3ull) * 8ull;
-  r.pos = r.start;
   r.end = r.start + nbytes * 8ull;
   // last word that lies entirely inside the caller's buffer
-  const uint64_t lastb = reinterpret_cast<uint64_t>(buf_end);
-  const uint64_t words = (lastb - (a & ~(uint64_t)3)) >> 2;
-  r.last_word = words ? (uint32_t)(words - 1ull > 0xFFFFFFFEull ? 0xFFFFFFFEull : words - 1ull) : 0u;
+  const uint64_t words = (reinterpret_cast<uint64_t>(buf_end) - (a & ~(uint64_t)3)) >> 2;
+  r.last_word = words ? (uint32_t)(words - 1ull > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : words - 1ull) : 0u;
+  rd_seek(r, r.start);
 }
-__device__ __forceinline__ uint32_t rd_word(const BitRd& r, u64 wi) {
-  const uint32_t i = wi > (u64)r.last_word ? r.last_word : (uint32_t)wi;
-  return __byte_perm(__ldg(r.base + i), 0u, 0x0123);
-}
-// the next 64 bits
-__device__ __forceinline__ u64 rd_peek(const BitRd& r) {
-  const u64 wi = r.pos >> 5;
-  const uint32_t sh = (uint32_t)r.pos & 31u;
-  const uint32_t w0 = rd_word(r, wi), w1 = rd_word(r, wi + 1ull), w2 = rd_word(r, wi + 2ull);
-  const uint32_t hi = __funnelshift_l(w1, w0, sh), lo = __funnelshift_l(w2, w1, sh);
-  return ((u64)hi << 32) | lo;
-}
+__device__ __forceinline__ bool rd_over(const BitRd& r) { return rd_pos(r) > r.end; }
 // n in [0,32]
 __device__ __forceinline__ uint32_t rd_get(BitRd& r, uint32_t n) {
-  if (n == 0u) return 0u;
-  const u64 w = rd_peek(r);
-  r.pos += n;
-  return (uint32_t)(w >> (64u - n));
+  rd_refill(r);
+  const uint32_t v = n ? (uint32_t)(r.w >> (64u - n)) : 0u;
+  r.w <<= n;
+  r.avail -= n;
+  return v;
 }
-__device__ __forceinline__ bool rd_over(const BitRd& r) { return r.pos > r.end; }
 
 // read_rice_unsigned (block/decoder.cpp:74-83): unary quotient limited to
 // UINT32_MAX >> k ones (read_unary_ones, bit_reader.hpp:140-172), then k remainder bits.
+// Does not test for the end of data on the fast path: callers check rd_over() per segment.
 __device__ __forceinline__ bool rd_rice(BitRd& r, uint32_t k, uint32_t* value) {
-  const u64 w = rd_peek(r);
-  const uint32_t hi = (uint32_t)(w >> 32);
+  rd_refill(r);
+  const uint32_t hi = (uint32_t)(r.w >> 32);
   uint32_t q;
-  if (hi != 0xFFFFFFFFu) {  // fast path: terminator within 32 bits, q + 1 + k <= 63
+  if (hi != 0xFFFFFFFFu) {  // terminator within the 32 bits in view
     q = (uint32_t)__clz((int)~hi);
-    const uint32_t rem = k ? (uint32_t)((w << (q + 1u)) >> (64u - k)) : 0u;
-    r.pos += q + 1u + k;
-    if (q > (0xFFFFFFFFu >> k) || r.pos > r.end) return false;
-    *value = (q << k) | rem;
-    return true;
-  }
-  // long unary run: walk word by word
-  const uint32_t max_ones = 0xFFFFFFFFu >> k;
-  q = 0u;
-  for (;;) {
-    const uint32_t top = (uint32_t)(rd_peek(r) >> 32);
-    const uint32_t run = (uint32_t)__clz((int)~top);
-    if (run < 32u) {
-      q += run;
-      r.pos += run + 1u;
-      break;
+    r.w <<= (q + 1u);
+    r.avail -= q + 1u;
+  } else {  // long unary run: walk word by word
+    const uint32_t max_ones = 0xFFFFFFFFu >> k;
+    q = 0u;
+    for (;;) {
+      rd_refill(r);
+      const uint32_t top = (uint32_t)(r.w >> 32);
+      const uint32_t run = (uint32_t)__clz((int)~top);
+      if (run < 32u) {
+        q += run;
+        r.w <<= (run + 1u);
+        r.avail -= run + 1u;
+        break;
+      }
+      q += 32u;
+      r.w <<= 32;
+      r.avail -= 32u;
+      if (q > max_ones || rd_over(r)) return false;
     }
-    q += 32u;
-    r.pos += 32u;
-    if (r.pos > r.end || q > max_ones) return false;
   }
-  if (q > max_ones || r.pos > r.end) return false;
-  const uint32_t rem = rd_get(r, k);
-  if (r.pos > r.end) return false;
+  rd_refill(r);
+  const uint32_t rem = k ? (uint32_t)(r.w >> (64u - k)) : 0u;
+  r.w <<= k;
+  r.avail -= k;
   *value = (q << k) | rem;
-  return true;
+  return q <= (0xFFFFFFFFu >> k);
 }
 
 // Incremental adaptive-k state (rice.hpp:15-114).  ring[] is the 256-entry window of
@@ -175,8 +197,9 @@ __device__ __forceinline__ bool decode_segment(BitRd& r, uint32_t n, uint32_t k0
       uint32_t u;
       if (!rd_rice(r, k0, &u)) return false;
       res[i] = unzz32(u);
+      if ((i & 255u) == 255u && rd_over(r)) return false;  // bounds the work on truncated streams
     }
-    return true;
+    return !rd_over(r);
   }
   KState st;
   ks_reset(st);
@@ -188,8 +211,9 @@ __device__ __forceinline__ bool decode_segment(BitRd& r, uint32_t n, uint32_t k0
       if (!rd_rice(r, k, &u)) return false;
       res[idx++] = unzz32(u);
       k = ks_step<STATELESS>(st, u, ring);
+      if ((idx & 255u) == 0u && rd_over(r)) return false;
     }
-    return true;
+    return !rd_over(r);
   }
   if (mode == MODE_BIN) {
     while (idx < n) {
@@ -206,7 +230,7 @@ __device__ __forceinline__ bool decode_segment(BitRd& r, uint32_t n, uint32_t k0
       res[idx++] = unzz32(u);
       k = ks_step<STATELESS>(st, u, ring);
     }
-    return true;
+    return !rd_over(r);
   }
   // MODE_ZR
   while (idx < n) {
@@ -234,7 +258,7 @@ __device__ __forceinline__ bool decode_segment(BitRd& r, uint32_t n, uint32_t k0
     res[idx++] = unzz32(u);
     k = ks_step<STATELESS>(st, u, ring);
   }
-  return true;
+  return !rd_over(r);
 }
 
 __device__ __forceinline__ uint32_t part_len(uint32_t n, uint32_t p, uint32_t idx) {
@@ -284,20 +308,19 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
   const uint32_t cnt = 1u << p;
   // the partition table sits in front of the tokens (block/decoder.cpp:447-455): remember
   // where it starts and read each entry when its segment comes up
-  const u64 table_pos = r.pos;
-  r.pos += 7ull * cnt;
-  if (rd_over(r)) return false;
-  const u64 tokens_pos = r.pos;
-  r.pos = table_pos;
-  const uint32_t first = rd_get(r, 7u);
-  if ((first >> 5) != cmode) return false;
-  r.pos = tokens_pos;
+  const u64 table_pos = rd_pos(r);
+  const u64 tokens_pos = table_pos + 7ull * cnt;
+  if (tokens_pos > r.end) return false;
+  if ((rd_get(r, 7u) >> 5) != cmode) return false;
+  rd_seek(r, tokens_pos);
   uint32_t off = 0u;
   for (uint32_t i = 0; i < cnt; ++i) {
-    const u64 save = r.pos;
-    r.pos = table_pos + 7ull * i;
-    const uint32_t mk = rd_get(r, 7u);
-    r.pos = save;
+    uint32_t mk;
+    {
+      BitRd t = r;  // table entry i (the reader is a handful of registers)
+      rd_seek(t, table_pos + 7ull * i);
+      mk = rd_get(t, 7u);
+    }
     const uint32_t len = part_len(n, p, i);
     const bool ok = p ? decode_segment<true>(r, len, mk & 31u, mk >> 5, out + off, ring)
                       : decode_segment<false>(r, len, mk & 31u, mk >> 5, out + off, ring);
@@ -305,10 +328,52 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
     off += len;
   }
   // consume_zero_padding_to_byte (bit_reader.hpp:180-185)
-  const uint32_t padn = (uint32_t)((8ull - ((r.pos - r.start) & 7ull)) & 7ull);
+  const uint32_t padn = (uint32_t)((8ull - ((rd_pos(r) - r.start) & 7ull)) & 7ull);
   if (padn) {
     if (rd_get(r, padn) != 0u) return false;
     if (rd_over(r)) return false;
+  }
+  return true;
+}
+
+// Runs step(i, value&) over x[0..n) in order, 8 samples at a time: the next chunk's loads
+// are issued before the current chunk's dependent arithmetic (the in-place pattern
+// load x[i] -> store x[i] otherwise pays a full memory round trip per sample), and the
+// chunks move as 128-bit vectors when the plane is 16-byte aligned.
+template <typename Step>
+__device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, Step&& step) {
+  const bool aligned = (reinterpret_cast<uint64_t>(x) & 15ull) == 0ull;
+  int32_t v[8], nv[8];
+  auto load8 = [&](uint32_t i, int32_t (&d)[8]) {
+    if (aligned) {
+      const int4 a = *reinterpret_cast<const int4*>(x + i), b = *reinterpret_cast<const int4*>(x + i + 4);
+      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = x[i + j];
+    }
+  };
+  uint32_t i = 0;
+  if (n >= 8u) load8(0u, v);
+  for (; i + 8u <= n; i += 8u) {
+    if (i + 16u <= n) load8(i + 8u, nv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (!step(i + (uint32_t)j, v[j])) return false;
+    if (aligned) {
+      *reinterpret_cast<int4*>(x + i) = make_int4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<int4*>(x + i + 4) = make_int4(v[4], v[5], v[6], v[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i + j] = v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = nv[j];
+  }
+  for (; i < n; ++i) {
+    int32_t t = x[i];
+    if (!step(i, t)) return false;
+    x[i] = t;
   }
   return true;
 }
@@ -318,8 +383,8 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
   if (type == PRED_FIXED) {
     if (order == 0u) return true;
     i64 h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-      i64 s = x[i];
+    return restore_chunked(x, n, [&](uint32_t i, int32_t& val) {
+      i64 s = val;
       if (i >= order) {
         i64 p;
         if (order == 1u) p = h1;
@@ -328,24 +393,24 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
         else p = 4 * h1 - 6 * h2 + 4 * h3 - h4;
         s += p;
         if (s < -2147483648ll || s > 2147483647ll) return false;
-        x[i] = (int32_t)s;
+        val = (int32_t)s;
       }
       h4 = h3; h3 = h2; h2 = h1; h1 = s;
-    }
-    return true;
+      return true;
+    });
   }
   if (type == PRED_FIR) {
     i64 h1 = 0, h2 = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-      i64 s = x[i];
+    return restore_chunked(x, n, [&](uint32_t i, int32_t& val) {
+      i64 s = val;
       if (i >= 2u) {
         s += (3 * h1 - h2) >> 2;
         if (s < -2147483648ll || s > 2147483647ll) return false;
-        x[i] = (int32_t)s;
+        val = (int32_t)s;
       }
       h2 = h1; h1 = s;
-    }
-    return true;
+      return true;
+    });
   }
   if (order <= 12u) {
     // history before the block start is zero, which reproduces taps = min(order, i)
@@ -355,18 +420,20 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
     int32_t h[13];
 #pragma unroll
     for (int t = 0; t <= 12; ++t) h[t] = 0;
-    for (uint32_t i = 0; i < n; ++i) {
+    return restore_chunked(x, n, [&](uint32_t, int32_t& val) {
+      // taps 2..12 do not depend on the previous sample: only c1*h1 sits on the serial chain
       i64 acc = 0;
 #pragma unroll
-      for (int t = 1; t <= 12; ++t) acc += (i64)cf[t] * (i64)h[t];
-      const i64 s = (acc >> 15) + (i64)x[i];
+      for (int t = 2; t <= 12; ++t) acc += (i64)cf[t] * (i64)h[t];
+      acc += (i64)cf[1] * (i64)h[1];
+      const i64 s = (acc >> 15) + (i64)val;
       if (s < -2147483648ll || s > 2147483647ll) return false;
-      x[i] = (int32_t)s;
+      val = (int32_t)s;
 #pragma unroll
       for (int t = 12; t >= 2; --t) h[t] = h[t - 1];
       h[1] = (int32_t)s;
-    }
-    return true;
+      return true;
+    });
   }
   for (uint32_t i = 0; i < n; ++i) {  // orders 13..32: legal in the format, never produced by the encoder
     i64 acc = 0;
@@ -386,8 +453,8 @@ struct DecCfg {
 // K12a: one warp per frame-block, lane 0 parses.  blk_fs[b] = first sample of block b,
 // blk_size[b] its sample count, blk_boff[b] its byte offset inside `payload`,
 // blk_bytes[b] its byte size.  Residuals go to the planes, predictor headers to hdrs[2b+ch].
-constexpr int kParseWarps = 2;
-__global__ void __launch_bounds__(32 * kParseWarps) k_parse_blocks(
+constexpr int kParseWarps = 1;
+__global__ void __launch_bounds__(32 * kParseWarps, 32) k_parse_blocks(
     DecCfg cfg, const uint8_t* __restrict__ payload, u64 payload_bytes, const u64* __restrict__ blk_fs,
     const uint32_t* __restrict__ blk_size, const u64* __restrict__ blk_boff, const uint32_t* __restrict__ blk_bytes,
     int32_t* L, int32_t* R, ChanHdr* hdrs, uint32_t* blk_err, uint8_t* blk_ms) {
@@ -412,7 +479,7 @@ __global__ void __launch_bounds__(32 * kParseWarps) k_parse_blocks(
   if (!err && !parse_channel_block(r, n, L + blk_fs[b], hdrs + (size_t)b * 2u, ring)) err = DERR_PRIMARY;
   if (!err && cfg.channels == 2u && !parse_channel_block(r, n, R + blk_fs[b], hdrs + (size_t)b * 2u + 1u, ring))
     err = DERR_SECONDARY;
-  if (!err && r.pos != r.end) err = DERR_TRAILING;  // checked after reconstruction in the reference
+  if (!err && rd_pos(r) != r.end) err = DERR_TRAILING;  // checked after reconstruction in the reference
   blk_err[b] = err;
   blk_ms[b] = (uint8_t)ms;
 }

@@ -277,6 +277,10 @@ static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) {
   sh &= 31u;
   return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
 }
+static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned sh) {
+  if (sh >= 32u) return lo;
+  return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+}
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
   sh &= 31u;
   return sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
