@@ -347,23 +347,23 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
     const uint32_t n = jd.n;
     load_block<NT, E>(sm, src, jd.kind, jd.start, n);
     __syncthreads();
-    int32_t x[E + 12];
-    load_items<NT, E>(sm, x);
     const uint32_t max_valid = n > 1u ? (n - 1u < 32u ? n - 1u : 32u) : 0u;
     const LpcQ* lq = lpcq + slot;
+    if (!PROBE && tid < 11u) recs[slot].cand_lo[tid] = 0xFFFFFFFFu;
 
     BestCand best;
     best.have = false;
     best.rice = best.zr = best.bin = best.stat = best.best = 0ull;
     best.type = best.order = best.taps = best.ci = best.k_init = best.k_stat = best.has_run = 0u;
-    uint32_t cand_lo[11];
-#pragma unroll
-    for (int i = 0; i < 11; ++i) cand_lo[i] = 0xFFFFFFFFu;
-
     // candidate order: fixed 0..4, FIR, LPC 4,6,8,10,12 (block/encoder.cpp:362-407)
     for (uint32_t ci = 0; ci < 11u; ++ci) {
       int32_t r[E];
       uint32_t type, order, taps = 0u;
+      {
+        // the samples are re-read from the X plane for every candidate instead of living in
+        // 28 registers across the whole search
+        int32_t x[E + 12];
+        load_items<NT, E>(sm, x);
       if (ci <= 4u) {
         type = PRED_FIXED;
         order = ci;
@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
         }
         if (taps == 0u) continue;  // block/encoder.cpp:402-404
       }
+      }
       Prep<NT, E> pr;
       prepare<NT, E, false>(sm, r, n, pr);
       if (tid == 0u) {
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
       const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
       const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
       const u64 bb = m1 < m2 ? m1 : m2;
-      cand_lo[ci] = (uint32_t)bb;
+      if (!PROBE && tid == 0u) recs[slot].cand_lo[ci] = (uint32_t)bb;
       if (!best.have || bb < best.best || (bb == best.best && type < best.type)) {  // :352-359
         best.have = true;
         best.rice = rice; best.zr = zr; best.bin = bin; best.stat = stat; best.best = bb;
@@ -432,7 +433,11 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
     // winner residual again, with the full prefix structures for the partition search
     const int16_t* wcoef = best.type == PRED_LPC ? lq->coef[best.ci - 6u] : nullptr;
     int32_t r[E];
-    compute_residual<NT, E>(x, g0, n, best.type, best.order, best.taps, wcoef, r);
+    {
+      int32_t x[E + 12];
+      load_items<NT, E>(sm, x);
+      compute_residual<NT, E>(x, g0, n, best.type, best.order, best.taps, wcoef, r);
+    }
     Prep<NT, E> pr;
     prepare<NT, E, true>(sm, r, n, pr);
 
@@ -514,13 +519,12 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
     const uint32_t nparts = 1u << best_p;
     u64 tok_bits = 0ull;
     {
-      const SegGeom sg = seg_geom(g0, n, best_p);
-      uint8_t kn[E];
+      const SegGeom sg = seg_geom<E>(g0, n, best_p);
       const uint8_t* mk = sm.SelMK();
       const uint32_t mkA = mk[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? mk[sg.sidA + 1u] : 0u;
-      if (best_p == 0u) k_series<NT, E, true>(sm, pr, n, sg, kn);
-      else k_series<NT, E, false>(sm, pr, n, sg, kn);
-      walk_items<NT, E>(sm, pr, n, sg, kn, mkA & 31u, mkB & 31u,
+      if (best_p == 0u) k_series<NT, E, true>(sm, pr, n, sg);
+      else k_series<NT, E, false>(sm, pr, n, sg);
+      walk_items<NT, E>(sm, pr, n, sg, mkA & 31u, mkB & 31u,
                         [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
                             bool long_run) {
                           const uint32_t m = inB ? mkB : mkA;
@@ -547,7 +551,6 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
         rec->taps = (uint8_t)best.taps;
         for (int i = 0; i < 13; ++i) rec->coef[i] = (wcoef && i >= 1 && (uint32_t)i <= chosen_order) ? wcoef[i] : (int16_t)0;
         rec->pad = 0;
-        for (int i = 0; i < 11; ++i) rec->cand_lo[i] = cand_lo[i];
       }
     }
     __syncthreads();
@@ -665,13 +668,12 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
       sm.SegP()[sid] = p ? prefix_u<NT, E>(sm, s * (n >> p)) : 0ull;
     }
     __syncthreads();
-    const SegGeom sg = seg_geom(g0, n, p);
-    uint8_t kn[E];
+    const SegGeom sg = seg_geom<E>(g0, n, p);
     const uint32_t mkA = sm.SelMK()[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? sm.SelMK()[sg.sidA + 1u] : 0u;
-    if (p == 0u) k_series<NT, E, true>(sm, pr, n, sg, kn);
-    else k_series<NT, E, false>(sm, pr, n, sg, kn);
+    if (p == 0u) k_series<NT, E, true>(sm, pr, n, sg);
+    else k_series<NT, E, false>(sm, pr, n, sg);
     u64 my_bits = 0ull;
-    walk_items<NT, E>(sm, pr, n, sg, kn, mkA & 31u, mkB & 31u,
+    walk_items<NT, E>(sm, pr, n, sg, mkA & 31u, mkB & 31u,
                       [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes, bool long_run) {
                         const uint32_t m = inB ? mkB : mkA;
                         bool emit;
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
       const i64 t0 = rel0 + (i64)hdr_bits + (i64)my_ex;
       if (my_bits && t0 < (i64)W * 32 && t0 + (i64)my_bits > 0) {
         i64 pos = t0;
-        walk_items<NT, E>(sm, pr, n, sg, kn, mkA & 31u, mkB & 31u,
+        walk_items<NT, E>(sm, pr, n, sg, mkA & 31u, mkB & 31u,
                           [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
                               bool long_run) {
                             const uint32_t m = inB ? mkB : mkA;

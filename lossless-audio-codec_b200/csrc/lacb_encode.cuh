@@ -79,7 +79,7 @@ struct ASmem {
   static constexpr size_t oCpre = oPthr + (((size_t)(NT + 1) * 8 + 15) & ~(size_t)15);
   static constexpr size_t oFlg = oCpre + (size_t)(NT + 1) * 32;
   static constexpr size_t oKpub = oFlg + (size_t)NT * 4;
-  static constexpr size_t oScr = oKpub + (size_t)NT * 4;
+  static constexpr size_t oScr = oKpub + (size_t)NT * E;
   static constexpr size_t oSegP = oScr + 40 * 8;
   static constexpr size_t oSegStat = oSegP + (MAXSEG + 1) * 8;
   static constexpr size_t oSelBits = oSegStat + (MAXSEG + 1) * 8;
@@ -95,7 +95,7 @@ struct ASmem {
   __device__ u64* Pthr() const { return reinterpret_cast<u64*>(base + oPthr); }
   __device__ PlaneCounts* Cpre() const { return reinterpret_cast<PlaneCounts*>(base + oCpre); }
   __device__ uint32_t* Flg() const { return reinterpret_cast<uint32_t*>(base + oFlg); }
-  __device__ uint32_t* Kpub() const { return reinterpret_cast<uint32_t*>(base + oKpub); }
+  __device__ uint32_t* Kpl() const { return reinterpret_cast<uint32_t*>(base + oKpub); }  // k per sample, 1 byte each
   __device__ u64* Scr() const { return reinterpret_cast<u64*>(base + oScr); }
   __device__ u64* SegP() const { return reinterpret_cast<u64*>(base + oSegP); }
   __device__ u64* SegStat() const { return reinterpret_cast<u64*>(base + oSegStat); }
@@ -219,19 +219,31 @@ __device__ __forceinline__ bool residual_lpc(const int32_t (&x)[E + 12], uint32_
 // ---------------------------------------------------------------------------
 // Per-residual preparation: zig-zag, U plane, per-thread prefix of u, last-nonzero
 // scan and bit-plane counts (totals only, or the full per-thread prefix for the
-// partition search when FULL).
+// partition search when FULL).  Nothing per-sample stays in registers afterwards:
+// later phases re-read u from the U plane (4 LDS.128 per thread), which is what keeps
+// the 1024-thread CTA inside its 64-register budget without spilling.
 template <int NT, int E>
 struct Prep {
-  uint32_t u[E];
   u64 Pex;          // sum of u over all samples before this thread's chunk
   int32_t lnz_ex;   // index of the last non-zero residual before the chunk (-1: none)
   uint32_t zmask;   // bit j: sample g0+j exists and its residual is zero
 };
 
+template <int NT, int E>
+__device__ __forceinline__ void load_u(const ASmem<NT, E>& sm, uint32_t (&u)[E]) {
+  const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
+#pragma unroll
+  for (int c = 0; c < E / 4; ++c) {
+    const uint4 v = U4[swz_chunk(threadIdx.x * (E / 4) + c)];
+    u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+  }
+}
+
 template <int NT, int E, bool FULL>
 __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&r)[E], uint32_t n, Prep<NT, E>& pr) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
   AMisc* mi = sm.Misc();
+  uint32_t u[E];
   u64 S = 0;
   int32_t lastnz = -1;
   uint32_t zmask = 0;
@@ -239,7 +251,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   for (int j = 0; j < E; ++j) {
     const bool in = g0 + j < n;
     const uint32_t uu = in ? zz32(r[j]) : 0u;
-    pr.u[j] = uu;
+    u[j] = uu;
     S += uu;
     if (uu) lastnz = (int32_t)(g0 + j);
     if (in && uu == 0u) zmask |= 1u << j;
@@ -248,11 +260,13 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   uint4* U4 = reinterpret_cast<uint4*>(sm.U());
 #pragma unroll
   for (int c = 0; c < E / 4; ++c)
-    U4[swz_chunk(tid * (E / 4) + c)] = make_uint4(pr.u[4 * c], pr.u[4 * c + 1], pr.u[4 * c + 2], pr.u[4 * c + 3]);
+    U4[swz_chunk(tid * (E / 4) + c)] = make_uint4(u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
   if (!FULL && tid < 8) {
     mi->cnt_tot[tid] = 0u;
     mi->cnt_first[tid] = 0u;
   }
+  uint32_t V[5];
+  csa_count<E>(u, V);
   __syncthreads();
   u64 total;
   pr.Pex = block_excl_scan_u64<NT>(S, sm.Scr(), &total);
@@ -265,8 +279,6 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   if (NT * E > 256 && g0 == 256u) mi->p_first = pr.Pex;
   pr.lnz_ex = block_excl_max_i32<NT>(lastnz, reinterpret_cast<int32_t*>(sm.Scr()));
 
-  uint32_t V[5];
-  csa_count<E>(pr.u, V);
   PlaneCounts pc;
   planes_from_sliced(V, pc);
   if (FULL) {
@@ -317,7 +329,9 @@ struct SegGeom {
   uint32_t a0;     // its first sample
   uint32_t bnd;    // first sample of the next segment (0xFFFFFFFF when none)
   uint32_t s0;     // segment number inside the level
+  bool fast;       // all E samples exist and lie in segment A: per-item bounds checks vanish
 };
+template <int E>
 __device__ __forceinline__ SegGeom seg_geom(uint32_t g0, uint32_t n, uint32_t p) {
   SegGeom g;
   if (p == 0u) {
@@ -325,107 +339,144 @@ __device__ __forceinline__ SegGeom seg_geom(uint32_t g0, uint32_t n, uint32_t p)
     g.a0 = 0u;
     g.bnd = 0xFFFFFFFFu;
     g.s0 = 0u;
-    return g;
+  } else {
+    const uint32_t base = n >> p, cnt = 1u << p;
+    uint32_t s0 = g0 / base;
+    if (s0 > cnt - 1u) s0 = cnt - 1u;
+    g.s0 = s0;
+    g.sidA = cnt - 1u + s0;
+    g.a0 = s0 * base;
+    g.bnd = (s0 + 1u < cnt) ? g.a0 + base : 0xFFFFFFFFu;
   }
-  const uint32_t base = n >> p, cnt = 1u << p;
-  uint32_t s0 = g0 / base;
-  if (s0 > cnt - 1u) s0 = cnt - 1u;
-  g.s0 = s0;
-  g.sidA = cnt - 1u + s0;
-  g.a0 = s0 * base;
-  g.bnd = (s0 + 1u < cnt) ? g.a0 + base : 0xFFFFFFFFu;
+  g.fast = (g0 + E <= n) && (g.bnd >= g0 + E);
   return g;
 }
 
-// k series of one level: on return kn[j] is the Rice parameter the model yields
-// AFTER consuming sample g0+j (i.e. the k used for sample g0+j+1 unless that sample
-// starts a segment), and Kpub[tid] = kn[E-1].
+// Exact base k of the adaptive models without a division or a search:
+//   mean = floor(N / c), k = mean <= 1 ? 0 : min(31, bit_width(mean - 1))
+// With M = N - c >= c:  bit_width(mean - 1) = 1 + max{ s : (M >> s) >= c }, and that s is
+// bit_width(M) - bit_width(c), minus one when the shifted value falls short of c.
+__device__ __forceinline__ uint32_t kbase_clz(u64 N, uint32_t c) {
+  if (N < 2ull * c) return 0u;
+  const u64 M = N - c;
+  const uint32_t s0 = bitwidth64(M) - (32u - (uint32_t)__clz((int)c));
+  const uint32_t t = (uint32_t)(M >> s0);
+  const uint32_t kb = 1u + s0 - (t < c ? 1u : 0u);
+  return kb > 31u ? 31u : kb;
+}
+
+// k series of one level.  On return the K plane holds, for every sample i, the Rice
+// parameter the model yields AFTER consuming sample i (the k used for sample i+1 unless
+// that sample starts a segment).
 //   STATEFUL  : Rice::adapt_k with drift and micro windows (rice.hpp:45-114), p = 0
 //   !STATEFUL : adapt_k_stateless (block/encoder.cpp:72-77), restarted per segment
-template <int NT, int E, bool STATEFUL>
-__device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
-                                         const SegGeom& sg, uint8_t (&kn)[E]) {
+template <int NT, int E, bool STATEFUL, bool FAST>
+__device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                                const SegGeom& sg, uint32_t (&kpk)[E / 4], uint32_t& flg_out) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
+  uint32_t u[E];
+  load_u<NT, E>(sm, u);
   const u64 PaA = STATEFUL ? 0ull : sm.SegP()[sg.sidA];
-  const u64 PaB = (!STATEFUL && sg.bnd != 0xFFFFFFFFu) ? sm.SegP()[sg.sidA + 1u] : 0ull;
+  const u64 PaB = (!FAST && !STATEFUL && sg.bnd != 0xFFFFFFFFu) ? sm.SegP()[sg.sidA + 1u] : 0ull;
   u64 Pin = pr.Pex;
-  uint32_t hint = 0u;
   uint32_t flg = 0u;
+#pragma unroll
+  for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = 0u;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const uint32_t idx = g0 + j;
-    Pin += pr.u[j];
-    const bool inB = idx >= sg.bnd;
+    Pin += u[j];
+    const bool inB = !FAST && idx >= sg.bnd;
     const uint32_t a = inB ? sg.bnd : sg.a0;
     const uint32_t c = idx - a + 1u;
     const u64 N = Pin - (inB ? PaB : PaA) + (c >> 1);
-    if (j == 0 || (inB && idx == sg.bnd)) hint = kbase_guess(N, c);
-    const uint32_t kb = kbase_from(N, c, hint);
-    hint = kb;
-    kn[j] = (uint8_t)kb;
+    const uint32_t kb = kbase_clz(N, c);
+    kpk[j >> 2] |= kb << (8 * (j & 3));
     if (STATEFUL) {
-      const uint32_t q = (kb >= 31u) ? 0u : (pr.u[j] >> kb);
-      if (idx < n) flg |= ((q > 3u) ? (1u << j) : 0u) | ((q == 0u) ? (1u << (16 + j)) : 0u);
+      const uint32_t q = (kb >= 31u) ? 0u : (u[j] >> kb);
+      if (FAST || idx < n) flg |= ((q > 3u) ? (1u << j) : 0u) | ((q == 0u) ? (1u << (16 + j)) : 0u);
     }
   }
+  flg_out = flg;
+}
+
+template <int NT, int E, bool FAST>
+__device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t flg,
+                                              uint32_t (&kpk)[E / 4]) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  uint32_t u[E];
+  load_u<NT, E>(sm, u);
+  const uint32_t* Flg = sm.Flg();
+  constexpr int D = (int)kMicroWin / E;       // threads spanned by the 96-sample micro window
+  constexpr int DW = (int)kDriftWin / E;      // threads spanned by the 256-sample drift window
+  uint32_t fullL = 0u, fullZ = 0u;
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    const uint32_t w = ((int)tid - d >= 0) ? Flg[tid - d] : 0u;
+    fullL += (uint32_t)__popc(w & 0xFFFFu);
+    fullZ += (uint32_t)__popc(w >> 16);
+  }
+  const uint32_t part = ((int)tid - D >= 0) ? Flg[tid - D] : 0u;
+  const int tt = (int)tid - DW;
+  u64 wprev = tt >= 0 ? sm.Pthr()[tt] : 0ull;  // becomes the inclusive prefix at item j of thread tt
+  const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
+  u64 Pin = pr.Pex;
+  uint32_t uw[4] = {0u, 0u, 0u, 0u};
+  // sliding micro-window counts: start with the window that ends just before item 0
+  uint32_t L = fullL + (uint32_t)__popc(part & 0xFFFFu), Z = fullZ + (uint32_t)__popc(part >> 16);
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const uint32_t c = g0 + j + 1u;
+    Pin += u[j];
+    if ((j & 3) == 0) {
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (tt >= 0) v = U4[swz_chunk((uint32_t)tt * (E / 4) + (uint32_t)(j >> 2))];
+      uw[0] = v.x; uw[1] = v.y; uw[2] = v.z; uw[3] = v.w;
+    }
+    wprev += uw[j & 3];
+    // item j enters the 96-sample window, item j of thread tid-D leaves it
+    L += ((flg >> j) & 1u) - ((part >> j) & 1u);
+    Z += ((flg >> (16 + j)) & 1u) - ((part >> (16 + j)) & 1u);
+    const u64 N = Pin + (c >> 1);
+    const uint32_t kb = (kpk[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+    int bias = 0;
+    if (c >= kDriftWin && N >= (u64)c) {
+      const u64 ws = Pin - wprev;          // sum of the last 256 u (wprev == 0 when tt < 0, c == 256)
+      const u64 lm = (ws + 128ull) >> 8;
+      const u64 tA = (3ull * lm + 3ull) >> 2;
+      if (N < tA * c) {
+        bias = 1;
+      } else {
+        const u64 tB = lm + 2ull + lm / 3ull;  // floor((4 lm + 3) / 3) + 1
+        if (N >= tB * c) bias = -1;
+      }
+    }
+    if (c >= kMicroWin) {
+      if (L * 4u >= 288u) bias = bias + 1 < 1 ? bias + 1 : 1;
+      else if (Z * 5u >= 384u) bias = bias - 1 > -1 ? bias - 1 : -1;
+    }
+    int k = (int)kb + bias;
+    k = k < 0 ? 0 : (k > 31 ? 31 : k);
+    kpk[j >> 2] = (kpk[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)k << (8 * (j & 3)));
+  }
+}
+
+template <int NT, int E, bool STATEFUL>
+__device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                         const SegGeom& sg) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t kpk[E / 4];
+  uint32_t flg;
+  if (sg.fast) k_series_thread<NT, E, STATEFUL, true>(sm, pr, n, sg, kpk, flg);
+  else k_series_thread<NT, E, STATEFUL, false>(sm, pr, n, sg, kpk, flg);
   if (STATEFUL) {
-    uint32_t* Flg = sm.Flg();
-    Flg[tid] = flg;
+    sm.Flg()[tid] = flg;
     __syncthreads();
-    constexpr int D = (int)kMicroWin / E;       // threads spanned by the 96-sample micro window
-    constexpr int DW = (int)kDriftWin / E;      // threads spanned by the 256-sample drift window
-    uint32_t fullL = 0u, fullZ = 0u;
-#pragma unroll
-    for (int d = 1; d < D; ++d) {
-      const uint32_t w = ((int)tid - d >= 0) ? Flg[tid - d] : 0u;
-      fullL += (uint32_t)__popc(w & 0xFFFFu);
-      fullZ += (uint32_t)__popc(w >> 16);
-    }
-    const uint32_t part = ((int)tid - D >= 0) ? Flg[tid - D] : 0u;
-    const int tt = (int)tid - DW;
-    u64 wprev = tt >= 0 ? sm.Pthr()[tt] : 0ull;  // becomes the inclusive prefix at item j of thread tt
-    const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
-    Pin = pr.Pex;
-    uint32_t uw[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < E; ++j) {
-      const uint32_t idx = g0 + j;
-      const uint32_t c = idx + 1u;
-      Pin += pr.u[j];
-      if ((j & 3) == 0) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (tt >= 0) v = U4[swz_chunk((uint32_t)tt * (E / 4) + (uint32_t)(j >> 2))];
-        uw[0] = v.x; uw[1] = v.y; uw[2] = v.z; uw[3] = v.w;
-      }
-      wprev += uw[j & 3];
-      const u64 N = Pin + (c >> 1);
-      const uint32_t kb = kn[j];
-      int bias = 0;
-      if (c >= kDriftWin && N >= (u64)c) {
-        const u64 ws = Pin - wprev;          // sum of the last 256 u (wprev == 0 when tt < 0, c == 256)
-        const u64 lm = (ws + 128ull) >> 8;
-        const u64 tA = (3ull * lm + 3ull) >> 2;
-        if (N < tA * c) {
-          bias = 1;
-        } else {
-          const u64 tB = lm + 2ull + lm / 3ull;  // floor((4 lm + 3) / 3) + 1
-          if (N >= tB * c) bias = -1;
-        }
-      }
-      if (c >= kMicroWin) {
-        const uint32_t low = (2u << j) - 1u;                 // items 0..j
-        const uint32_t high = (~low) & ((1u << E) - 1u);     // items j+1..E-1
-        const uint32_t L = fullL + (uint32_t)__popc(flg & low) + (uint32_t)__popc(part & high);
-        const uint32_t Z = fullZ + (uint32_t)__popc((flg >> 16) & low) + (uint32_t)__popc((part >> 16) & high);
-        if (L * 4u >= 288u) bias = bias + 1 < 1 ? bias + 1 : 1;
-        else if (Z * 5u >= 384u) bias = bias - 1 > -1 ? bias - 1 : -1;
-      }
-      int k = (int)kb + bias;
-      k = k < 0 ? 0 : (k > 31 ? 31 : k);
-      kn[j] = (uint8_t)k;
-    }
+    k_bias_thread<NT, E, true>(sm, pr, flg, kpk);
   }
-  sm.Kpub()[tid] = kn[E - 1];
+  uint32_t* K = sm.Kpl() + tid * (E / 4);
+#pragma unroll
+  for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];
   __syncthreads();
 }
 
@@ -473,14 +524,20 @@ __device__ __forceinline__ Token token_rice_unsigned(uint32_t u, uint32_t k, uin
   return t;
 }
 
-// Walks the thread's samples with the k series in place and calls
+// Walks the thread's samples with the k series in place (K plane) and calls
 //   f(j, idx, inB, u, k, is_zero, run_len_if_last /*0 unless this sample closes a run >= 4*/, in_long_run)
-template <int NT, int E, typename F>
-__device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
-                                           const SegGeom& sg, const uint8_t (&kn)[E], uint32_t kinitA,
-                                           uint32_t kinitB, F&& f) {
+template <int NT, int E, bool FAST, typename F>
+__device__ __forceinline__ void walk_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                            const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
-  if (g0 >= n) return;
+  uint32_t u[E];
+  load_u<NT, E>(sm, u);
+  uint32_t kpk[E / 4];
+  {
+    const uint32_t* K = sm.Kpl() + tid * (E / 4);
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = K[c4];
+  }
   const uint32_t zm_all = zero_lookahead(sm, pr, n);
   // samples at or after the segment boundary do not extend a run that started before it
   uint32_t zmA = zm_all;
@@ -491,15 +548,16 @@ __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT
     const uint32_t byseg = g0 - sg.a0;
     z = byscan < byseg ? byscan : byseg;
   }
-  uint32_t kprev = tid ? sm.Kpub()[tid - 1u] : 0u;
+  // k of the sample before this chunk (the last byte of the previous thread's K words)
+  uint32_t kprev = tid ? (sm.Kpl()[tid * (E / 4) - 1u] >> 24) : 0u;
+  if (g0 == sg.a0) kprev = kinitA;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const uint32_t idx = g0 + j;
-    if (idx < n) {
-      const bool inB = idx >= sg.bnd;
-      uint32_t k = (j == 0) ? kprev : (uint32_t)kn[j - 1];
-      if (idx == sg.a0) { k = kinitA; z = 0u; }
-      if (idx == sg.bnd) { k = kinitB; z = 0u; }
+    if (FAST || idx < n) {
+      const bool inB = !FAST && idx >= sg.bnd;
+      uint32_t k = (j == 0) ? kprev : ((kpk[(j - 1) >> 2] >> (8 * ((j - 1) & 3))) & 0xFFu);
+      if (!FAST && idx == sg.bnd) { k = kinitB; z = 0u; }
       const uint32_t zm = inB ? zm_all : zmA;
       const bool is_zero = (zm >> j) & 1u;
       z = is_zero ? z + 1u : 0u;
@@ -507,9 +565,16 @@ __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT
       const uint32_t fwd = (uint32_t)__ffs((int)~(zm >> (j + 1))) - 1u;
       const bool long_run = is_zero && (z + fwd >= kZrMinRun);
       const uint32_t closes = (long_run && fwd == 0u) ? z : 0u;
-      f(j, idx, inB, pr.u[j], k, is_zero, closes, long_run);
+      f(j, idx, inB, u[j], k, is_zero, closes, long_run);
     }
   }
+}
+template <int NT, int E, typename F>
+__device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                           const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
+  if (threadIdx.x * E >= n) return;
+  if (sg.fast) walk_thread<NT, E, true>(sm, pr, n, sg, kinitA, kinitB, f);
+  else walk_thread<NT, E, false>(sm, pr, n, sg, kinitA, kinitB, f);
 }
 
 // estimate_residual_costs (block/encoder.cpp:201-263) for one level.  STATEFUL writes
@@ -520,15 +585,14 @@ __device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT,
                                           uint32_t kinit_stateful) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
   AMisc* mi = sm.Misc();
-  const SegGeom sg = seg_geom(g0, n, STATEFUL ? 0u : p);
-  uint8_t kn[E];
+  const SegGeom sg = seg_geom<E>(g0, n, STATEFUL ? 0u : p);
   if (tid == 0) {
     mi->tot_rice = 0ull;
     mi->tot_zr = 0ull;
     mi->tot_bin = 0ull;
   }
   if (tid < 8) mi->hasrun_bits[tid] = 0u;
-  k_series<NT, E, STATEFUL>(sm, pr, n, sg, kn);  // ends with a barrier
+  k_series<NT, E, STATEFUL>(sm, pr, n, sg);  // ends with a barrier
   uint32_t kinitA, kinitB = 0u;
   if (STATEFUL) {
     kinitA = kinit_stateful;
@@ -538,7 +602,7 @@ __device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT,
   }
   u64 riceA = 0, zrA = 0, binA = 0, riceB = 0, zrB = 0, binB = 0;
   uint32_t runA = 0, runB = 0;
-  walk_items<NT, E>(sm, pr, n, sg, kn, kinitA, kinitB,
+  walk_items<NT, E>(sm, pr, n, sg, kinitA, kinitB,
                     [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
                         bool long_run) {
                       const u64 rc = rice_cost(u, k);
