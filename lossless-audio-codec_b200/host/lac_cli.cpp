@@ -1,0 +1,211 @@
+// lac_cli.cpp -- `lac_cli encode|decode|selftest` on the GPU path.
+//
+// Same workflow and flags as the reference CLI (src/main.cpp:600-918): --stereo-mode=lr|ms
+// (default: auto per block), --threads=N / LAC_THREADS, --debug-threads, --no-partitioning;
+// plus --devices=N / LAC_DEVICES to shard the block range across GPUs.  Files are written
+// to a private temporary name and published with rename(), and input == output is refused.
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "lac_host.hpp"
+#include "wav_io.hpp"
+
+namespace {
+
+void usage() {
+  std::cerr << "Usage:\n"
+            << "  lac_cli encode input.wav output.lac [--stereo-mode=lr|ms] [--threads=N] [--devices=N] "
+               "[--debug-threads] [--no-partitioning] [--allow-large]\n"
+            << "  lac_cli decode input.lac output.wav [--threads=N] [--debug-threads]\n"
+            << "  lac_cli selftest\n";
+}
+
+size_t parse_count_flag(const std::string& arg, const char* name) {
+  const std::string v = arg.substr(std::strlen(name));
+  if (v.empty()) throw std::invalid_argument(std::string(name) + " requires a positive integer");
+  for (char c : v)
+    if (c < '0' || c > '9') throw std::invalid_argument(std::string(name) + " requires a positive integer");
+  const unsigned long long n = std::stoull(v);
+  if (n == 0) throw std::invalid_argument(std::string(name) + " requires a positive integer");
+  return (size_t)n;
+}
+
+bool load_file(const std::string& path, std::vector<uint8_t>& out, uint64_t cap) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long long n = std::ftell(f);
+  std::rewind(f);
+  bool ok = n >= 0 && (uint64_t)n <= cap;
+  if (ok) {
+    out.resize((size_t)n);
+    ok = n == 0 || std::fread(out.data(), 1, (size_t)n, f) == (size_t)n;
+  }
+  std::fclose(f);
+  return ok;
+}
+
+// write to "<path>.tmp.<pid>" and rename over the destination only when complete
+struct Staged {
+  std::string final_path, tmp_path;
+  explicit Staged(const std::string& p) : final_path(p), tmp_path(p + ".tmp." + std::to_string((long)getpid())) {}
+  bool publish() { return std::rename(tmp_path.c_str(), final_path.c_str()) == 0; }
+  ~Staged() { std::remove(tmp_path.c_str()); }
+};
+
+bool save_file(const std::string& path, const std::vector<uint8_t>& bytes) {
+  FILE* f = std::fopen(path.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = bytes.empty() || std::fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
+  return (std::fclose(f) == 0) && ok;
+}
+
+void print_threads(const char* label, const LAC::ThreadCollector& tc) {
+  const auto ids = tc.snapshot();
+  std::cout << label << ": " << ids.size() << " threads\n";
+  for (const auto& id : ids) std::cout << "  " << id << "\n";
+  std::cout << "GPU devices visible: " << lacb_host::device_count() << "\n";
+}
+
+int selftest() {
+  const double pi = 3.14159265358979323846;
+  for (uint32_t sr : {44100u, 48000u, 96000u, 192000u})
+    for (uint8_t depth : {(uint8_t)16, (uint8_t)24}) {
+      const size_t n = sr / 20 + 37;
+      const double amp = depth == 16 ? 12000.0 : 2.6e6;
+      std::vector<int32_t> l(n), r(n);
+      for (size_t i = 0; i < n; ++i) {
+        l[i] = (int32_t)std::lround(amp * std::sin(2 * pi * 440.0 * (double)i / sr));
+        r[i] = (int32_t)std::lround(amp * 0.9 * std::sin(2 * pi * 443.0 * (double)i / sr));
+      }
+      for (int mode = 0; mode <= 3; ++mode) {  // LR, MS, auto, mono
+        LAC::Encoder enc(12, (uint8_t)(mode == 3 ? 0 : mode), sr, depth);
+        const std::vector<int32_t> none;
+        const std::vector<uint8_t> bs = enc.encode(l, mode == 3 ? none : r);
+        LAC::Decoder dec;
+        std::vector<int32_t> dl, dr;
+        FrameHeader hdr;
+        const auto t0 = std::chrono::steady_clock::now();
+        dec.decode(bs.data(), bs.size(), dl, dr, &hdr);
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        const bool ok = dl == l && (mode == 3 ? dr.empty() : dr == r) && hdr.sample_rate == sr && hdr.bit_depth == depth &&
+                        hdr.channels == (mode == 3 ? 1 : 2) && hdr.stereo_mode == (mode == 3 ? 0 : mode);
+        if (!ok) {
+          std::cerr << "Selftest mismatch sr=" << sr << " depth=" << int(depth) << " mode=" << mode << "\n";
+          return 1;
+        }
+        if (mode == 2)
+          std::cout << "Selftest sr=" << sr << "Hz depth=" << int(depth) << " bytes=" << bs.size() << " decode_us=" << us << "\n";
+      }
+    }
+  std::cout << "Selftest complete: adaptive block tests passed.\n";
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  try {
+    if (argc < 2) {
+      usage();
+      return 1;
+    }
+    const std::string cmd = argv[1];
+    if (cmd == "selftest") return selftest();
+    if ((cmd != "encode" && cmd != "decode") || argc < 4) {
+      usage();
+      return 1;
+    }
+    const std::string in_path = argv[2], out_path = argv[3];
+    if (in_path == out_path) {
+      std::cerr << "Input and output paths must be different\n";
+      return 1;
+    }
+    uint8_t stereo_mode = 2;
+    size_t threads = 0, devices = 0;
+    bool debug_threads = false, partitioning = true, allow_large = false;
+    for (int i = 4; i < argc; ++i) {
+      const std::string a = argv[i];
+      if (a == "--stereo-mode=lr") stereo_mode = 0;
+      else if (a == "--stereo-mode=ms") stereo_mode = 1;
+      else if (a == "--stereo-mode=auto") stereo_mode = 2;
+      else if (a.rfind("--threads=", 0) == 0) threads = parse_count_flag(a, "--threads=");
+      else if (a.rfind("--devices=", 0) == 0) devices = parse_count_flag(a, "--devices=");
+      else if (a == "--debug-threads") debug_threads = true;
+      else if (a == "--no-partitioning") partitioning = false;
+      else if (a == "--allow-large") allow_large = true;
+      else if (a == "--debug-lpc" || a == "--debug-stereo-est" || a == "--debug-zr" || a == "--debug-partitions") {
+      } else {
+        std::cerr << "Unknown option: " << a << "\n";
+        usage();
+        return 1;
+      }
+    }
+    if (threads == 0) threads = LAC::parse_thread_limit(std::getenv("LAC_THREADS"));
+
+    if (cmd == "encode") {
+      WavInfo info;
+      std::vector<uint8_t> pcm;
+      if (!read_wav_packed(in_path, info, pcm, allow_large)) {
+        std::cerr << "Failed to read WAV: " << in_path << "\n";
+        return 1;
+      }
+      LAC::ThreadCollector tc;
+      LAC::Encoder enc(12, stereo_mode, info.sample_rate, info.bit_depth);
+      enc.set_partitioning_enabled(partitioning);
+      enc.set_thread_count(threads);
+      enc.set_device_count(devices);
+      const std::vector<uint8_t> bitstream = enc.encode_packed(pcm.data(), info.frames, (uint8_t)info.channels, &tc);
+      Staged st(out_path);
+      if (!save_file(st.tmp_path, bitstream) || !st.publish()) {
+        std::cerr << "Failed to write LAC file: " << out_path << "\n";
+        return 1;
+      }
+      std::cout << "Encoded " << in_path << " -> " << out_path << " (" << bitstream.size() << " bytes)\n";
+      if (debug_threads) print_threads("Thread usage", tc);
+      return 0;
+    }
+
+    std::vector<uint8_t> lac;
+    if (!load_file(in_path, lac, 1ull << 30)) {
+      std::cerr << "Failed to read LAC file: " << in_path << "\n";
+      return 1;
+    }
+    LAC::ThreadCollector tc;
+    LAC::Decoder dec(&tc);
+    dec.set_thread_count(threads);
+    std::vector<uint8_t> pcm;
+    FrameHeader hdr;
+    uint64_t frames = 0;
+    try {
+      dec.decode_packed(lac.data(), lac.size(), pcm, hdr, frames);
+    } catch (const std::runtime_error& e) {
+      std::cerr << "Decode failed: " << e.what() << "\n";
+      return 1;
+    }
+    WavInfo info;
+    info.channels = hdr.channels;
+    info.sample_rate = hdr.sample_rate;
+    info.bit_depth = hdr.bit_depth;
+    info.frames = frames;
+    Staged st(out_path);
+    if (!write_wav_packed(st.tmp_path, info, pcm.data(), pcm.size()) || !st.publish()) {
+      std::cerr << "Failed to write WAV: " << out_path << "\n";
+      return 1;
+    }
+    std::cout << "Decoded " << in_path << " -> " << out_path << " (" << frames << " samples per channel)\n";
+    if (debug_threads) print_threads("Decoder thread usage", tc);
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "Error: " << e.what() << "\n";
+    return 1;
+  }
+}

@@ -1,0 +1,30 @@
+// wav_io.hpp -- strict RIFF/WAVE PCM reader/writer of the host side.
+//
+// Accept/reject rules follow the reference parser (src/io/wav_io.cpp:162-278): RIFF size
+// must match the file, one 16-byte PCM fmt chunk before one non-empty data chunk, 16/24-bit,
+// 1-2 channels, 44.1/48/96/192 kHz, consistent block_align / byte_rate, unknown chunks
+// skipped, odd chunks padded.  Unlike the reference it keeps the samples as the packed
+// little-endian bytes of the data chunk (the GPU de-interleaves them)
+// instead of issuing one ifstream read per sample.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+struct WavInfo {
+  uint16_t channels = 0;
+  uint32_t sample_rate = 0;
+  uint8_t bit_depth = 0;
+  uint64_t frames = 0;
+};
+
+constexpr uint64_t kMaxDecodedPcmBytes = 1ull << 30;  // src/io/wav_io.cpp:13 (int32 planes)
+
+// pcm receives frames * channels * bit_depth/8 bytes.  allow_large lifts the reference's
+// 1 GiB decoded-PCM cap (needed for BASELINE configs 3 and 4).
+bool read_wav_packed(const std::string& path, WavInfo& info, std::vector<uint8_t>& pcm, bool allow_large = false);
+bool write_wav_packed(const std::string& path, const WavInfo& info, const uint8_t* pcm, uint64_t pcm_bytes);
+// int32 plane variants for callers that hold planes (LAC::Decoder::decode output)
+bool write_wav_planes(const std::string& path, const WavInfo& info, const std::vector<int32_t>& left,
+                      const std::vector<int32_t>& right);
+void unpack_planes(const WavInfo& info, const uint8_t* pcm, std::vector<int32_t>& left, std::vector<int32_t>& right);
