@@ -95,6 +95,13 @@ int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const voi
                 uint64_t frames, uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes,
                 lacb_err* err);
 
+/* Same, writing the payload into a caller buffer (use lacb_host_malloc memory to get full
+ * PCIe speed).  Returns LACB_ENOMEM and the required size in *payload_bytes when
+ * payload_cap is too small. */
+int lacb_encode_to(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
+                   uint64_t frames, uint8_t* payload_buf, uint64_t payload_cap, uint64_t* payload_bytes,
+                   uint32_t* block_bytes, lacb_err* err);
+
 /* Same, with the PCM already resident on this context's device (d_a / d_b as pcm_a /
  * pcm_b above, device pointers) and the results left there.  *d_payload and
  * *d_block_bytes point into the context's workspace and stay valid until the next call

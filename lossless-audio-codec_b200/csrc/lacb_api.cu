@@ -404,18 +404,18 @@ int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
   return 0;
 }
 
-int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
-                uint64_t frames, uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes,
-                lacb_err* err) {
+static int encode_host(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
+                       uint64_t frames, uint8_t* dst, uint64_t dst_cap, uint8_t** payload_out,
+                       uint64_t* payload_bytes, uint32_t* block_bytes, lacb_err* err) {
   if (!ctx) return LACB_EINVAL;
-  if (!params_ok(prm) || !pcm_a || frames == 0 || !payload_out || !payload_bytes ||
+  if (!params_ok(prm) || !pcm_a || frames == 0 || (!payload_out && !dst) || !payload_bytes ||
       (layout == LACB_PLANAR_I32 && prm->channels == 2 && !pcm_b) ||
       (layout != LACB_PLANAR_I32 && layout != LACB_PACKED_LE) || (frames + kMaxBlock - 1) / kMaxBlock > 0xFFFFFFu) {
     ctx->err = "invalid encode arguments";
     set_err(err, LACB_EINVAL, 0, 0, "invalid encode arguments");
     return LACB_EINVAL;
   }
-  *payload_out = nullptr;
+  if (payload_out) *payload_out = nullptr;
   *payload_bytes = 0;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -442,17 +442,41 @@ int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const voi
   }
   uint64_t total = 0;
   CKR(encode_on_device(ctx, prm, as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR), frames, validate, &total, err));
-  uint8_t* host = (uint8_t*)malloc(total ? total : 1);
-  if (!host) return LACB_ENOMEM;
+  uint8_t* host = dst;
+  if (dst) {
+    if (total > dst_cap) {  // tell the caller how much room the payload needs
+      *payload_bytes = total;
+      ctx->err = "payload buffer too small";
+      return LACB_ENOMEM;
+    }
+  } else {
+    host = (uint8_t*)malloc(total ? total : 1);
+    if (!host) return LACB_ENOMEM;
+  }
   CK(cudaMemcpyAsync(host, ctx->payload.p, total, cudaMemcpyDeviceToHost, st));
   if (block_bytes) CK(cudaMemcpyAsync(block_bytes, ctx->blk_bytes.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->ev[EV_D2H], st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   fill_enc_timing(ctx);
-  *payload_out = host;
+  if (payload_out) *payload_out = host;
   *payload_bytes = total;
   return 0;
+}
+
+int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
+                uint64_t frames, uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes,
+                lacb_err* err) {
+  if (!payload_out) return LACB_EINVAL;
+  return encode_host(ctx, prm, layout, pcm_a, pcm_b, frames, nullptr, 0, payload_out, payload_bytes, block_bytes, err);
+}
+
+int lacb_encode_to(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
+                   uint64_t frames, uint8_t* payload_buf, uint64_t payload_cap, uint64_t* payload_bytes,
+                   uint32_t* block_bytes, lacb_err* err) {
+  if (!payload_buf) return LACB_EINVAL;
+  return encode_host(ctx, prm, layout, pcm_a, pcm_b, frames, payload_buf, payload_cap, nullptr, payload_bytes,
+                     block_bytes, err);
 }
 
 int lacb_encode_block(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int zero_run, int partitioning, uint8_t** out,

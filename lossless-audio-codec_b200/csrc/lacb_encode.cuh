@@ -227,6 +227,7 @@ struct Prep {
   u64 Pex;          // sum of u over all samples before this thread's chunk
   int32_t lnz_ex;   // index of the last non-zero residual before the chunk (-1: none)
   uint32_t zmask;   // bit j: sample g0+j exists and its residual is zero
+  uint32_t any4;    // block-uniform: the residual contains a run of >= 4 zeros somewhere
 };
 
 template <int NT, int E>
@@ -238,6 +239,9 @@ __device__ __forceinline__ void load_u(const ASmem<NT, E>& sm, uint32_t (&u)[E])
     u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
   }
 }
+
+template <int NT, int E>
+__device__ __forceinline__ uint32_t zero_lookahead(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n);
 
 template <int NT, int E, bool FULL>
 __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&r)[E], uint32_t n, Prep<NT, E>& pr) {
@@ -303,6 +307,14 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     }
   }
   __syncthreads();
+  {
+    // any run of >= 4 zeros starting inside this chunk (look-ahead reaches 4 samples into the
+    // next chunk)?  Without one, no partition of any level can use a zero-run token and all
+    // run bookkeeping is skipped.
+    const uint32_t zm = zero_lookahead(sm, pr, n);
+    const uint32_t r4 = zm & (zm >> 1) & (zm >> 2) & (zm >> 3) & ((1u << E) - 1u);
+    pr.any4 = (uint32_t)__syncthreads_or((int)(r4 != 0u));
+  }
 }
 
 // prefix of u / of the plane counts at an arbitrary sample position (any thread)
@@ -382,6 +394,37 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
   uint32_t flg = 0u;
 #pragma unroll
   for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = 0u;
+  if (FAST) {
+    // One evaluation for the whole chunk when k provably does not change inside it:
+    // N_j is non-decreasing and c_j increases by one, so
+    //   N_first >= lo * c_last  and  N_last < hi * c_first   (lo = 2^(k-1)+1, hi = 2^k+1)
+    // bound every (N_j, c_j) of the chunk inside the k cell of the first sample.
+    const u64 S = sm.Pthr()[tid + 1u] - pr.Pex;
+    const uint32_t c_first = g0 - sg.a0 + 1u, c_last = c_first + (uint32_t)E - 1u;
+    const u64 rel = pr.Pex - PaA;
+    const u64 N_first = rel + u[0] + (c_first >> 1), N_last = rel + S + (c_last >> 1);
+    const uint32_t kb0 = kbase_clz(N_first, c_first);
+    bool uniform;
+    if (kb0 == 0u) {
+      uniform = N_last < 2ull * c_first;
+    } else {
+      const u64 lo = (1ull << (kb0 - 1u)) + 1ull, hi = (1ull << kb0) + 1ull;
+      uniform = (N_first >= lo * c_last) && (kb0 == 31u || N_last < hi * c_first);
+    }
+    if (uniform) {
+#pragma unroll
+      for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = kb0 * 0x01010101u;
+      if (STATEFUL) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const uint32_t q = (kb0 >= 31u) ? 0u : (u[j] >> kb0);
+          flg |= ((q > 3u) ? (1u << j) : 0u) | ((q == 0u) ? (1u << (16 + j)) : 0u);
+        }
+      }
+      flg_out = flg;
+      return;
+    }
+  }
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const uint32_t idx = g0 + j;
@@ -419,6 +462,27 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
   const uint32_t part = ((int)tid - D >= 0) ? Flg[tid - D] : 0u;
   const int tt = (int)tid - DW;
   u64 wprev = tt >= 0 ? sm.Pthr()[tt] : 0ull;  // becomes the inclusive prefix at item j of thread tt
+  {
+    // Cheap proof that every bias in this chunk is 0 (then the k series is the base series):
+    //  * micro window: even counting every flag of the 7 threads it can touch, neither
+    //    count reaches its threshold;
+    //  * drift window: with lm bounded by [W0 - S_leave, W0 + S_own] and (N, c) bounded as in
+    //    the k shortcut, neither comparison can fire.
+    const uint32_t c_first = g0 + 1u, c_last = g0 + (uint32_t)E;
+    const uint32_t Lub = fullL + (uint32_t)__popc(part & 0xFFFFu) + (uint32_t)__popc(flg & 0xFFFFu);
+    const uint32_t Zub = fullZ + (uint32_t)__popc(part >> 16) + (uint32_t)__popc(flg >> 16);
+    bool quiet = !(c_last >= kMicroWin && (Lub * 4u >= 288u || Zub * 5u >= 384u));
+    if (quiet && c_last >= kDriftWin) {
+      const u64 S_own = sm.Pthr()[tid + 1u] - pr.Pex;
+      const u64 S_leave = tt >= 0 ? sm.Pthr()[tt + 1] - sm.Pthr()[tt] : 0ull;
+      const u64 W0 = pr.Pex - wprev;
+      const u64 lm_max = (W0 + S_own + 128ull) >> 8, lm_min = (W0 - S_leave + 128ull) >> 8;
+      const u64 N_first = pr.Pex + u[0] + (c_first >> 1), N_last = pr.Pex + S_own + (c_last >> 1);
+      const u64 tA = (3ull * lm_max + 3ull) >> 2, tB = lm_min + 2ull + lm_min / 3ull;
+      quiet = (N_first >= tA * c_last) && (N_last < tB * c_first);
+    }
+    if (quiet) return;
+  }
   const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
   u64 Pin = pr.Pex;
   uint32_t uw[4] = {0u, 0u, 0u, 0u};
@@ -526,7 +590,7 @@ __device__ __forceinline__ Token token_rice_unsigned(uint32_t u, uint32_t k, uin
 
 // Walks the thread's samples with the k series in place (K plane) and calls
 //   f(j, idx, inB, u, k, is_zero, run_len_if_last /*0 unless this sample closes a run >= 4*/, in_long_run)
-template <int NT, int E, bool FAST, typename F>
+template <int NT, int E, bool FAST, bool ZR, typename F>
 __device__ __forceinline__ void walk_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                             const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
@@ -538,12 +602,12 @@ __device__ __forceinline__ void walk_thread(const ASmem<NT, E>& sm, const Prep<N
 #pragma unroll
     for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = K[c4];
   }
-  const uint32_t zm_all = zero_lookahead(sm, pr, n);
+  const uint32_t zm_all = ZR ? zero_lookahead(sm, pr, n) : 0u;
   // samples at or after the segment boundary do not extend a run that started before it
   uint32_t zmA = zm_all;
-  if (sg.bnd != 0xFFFFFFFFu && sg.bnd - g0 < (uint32_t)(E + 4)) zmA &= (1u << (sg.bnd - g0)) - 1u;
-  uint32_t z;  // zeros immediately before g0 inside the current segment
-  {
+  if (ZR && sg.bnd != 0xFFFFFFFFu && sg.bnd - g0 < (uint32_t)(E + 4)) zmA &= (1u << (sg.bnd - g0)) - 1u;
+  uint32_t z = 0u;  // zeros immediately before g0 inside the current segment
+  if (ZR) {
     const uint32_t byscan = g0 - 1u - (uint32_t)pr.lnz_ex;  // lnz_ex >= -1
     const uint32_t byseg = g0 - sg.a0;
     z = byscan < byseg ? byscan : byseg;
@@ -558,14 +622,18 @@ __device__ __forceinline__ void walk_thread(const ASmem<NT, E>& sm, const Prep<N
       const bool inB = !FAST && idx >= sg.bnd;
       uint32_t k = (j == 0) ? kprev : ((kpk[(j - 1) >> 2] >> (8 * ((j - 1) & 3))) & 0xFFu);
       if (!FAST && idx == sg.bnd) { k = kinitB; z = 0u; }
-      const uint32_t zm = inB ? zm_all : zmA;
-      const bool is_zero = (zm >> j) & 1u;
-      z = is_zero ? z + 1u : 0u;
-      // zeros following this sample inside the segment, at most 4 looked at
-      const uint32_t fwd = (uint32_t)__ffs((int)~(zm >> (j + 1))) - 1u;
-      const bool long_run = is_zero && (z + fwd >= kZrMinRun);
-      const uint32_t closes = (long_run && fwd == 0u) ? z : 0u;
-      f(j, idx, inB, u[j], k, is_zero, closes, long_run);
+      if (ZR) {
+        const uint32_t zm = inB ? zm_all : zmA;
+        const bool is_zero = (zm >> j) & 1u;
+        z = is_zero ? z + 1u : 0u;
+        // zeros following this sample inside the segment, at most 4 looked at
+        const uint32_t fwd = (uint32_t)__ffs((int)~(zm >> (j + 1))) - 1u;
+        const bool long_run = is_zero && (z + fwd >= kZrMinRun);
+        const uint32_t closes = (long_run && fwd == 0u) ? z : 0u;
+        f(j, idx, inB, u[j], k, is_zero, closes, long_run);
+      } else {
+        f(j, idx, inB, u[j], k, u[j] == 0u, 0u, false);
+      }
     }
   }
 }
@@ -573,8 +641,13 @@ template <int NT, int E, typename F>
 __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                            const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
   if (threadIdx.x * E >= n) return;
-  if (sg.fast) walk_thread<NT, E, true>(sm, pr, n, sg, kinitA, kinitB, f);
-  else walk_thread<NT, E, false>(sm, pr, n, sg, kinitA, kinitB, f);
+  if (pr.any4) {
+    if (sg.fast) walk_thread<NT, E, true, true>(sm, pr, n, sg, kinitA, kinitB, f);
+    else walk_thread<NT, E, false, true>(sm, pr, n, sg, kinitA, kinitB, f);
+  } else {
+    if (sg.fast) walk_thread<NT, E, true, false>(sm, pr, n, sg, kinitA, kinitB, f);
+    else walk_thread<NT, E, false, false>(sm, pr, n, sg, kinitA, kinitB, f);
+  }
 }
 
 // estimate_residual_costs (block/encoder.cpp:201-263) for one level.  STATEFUL writes
@@ -610,7 +683,9 @@ __device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT,
                       if (is_zero) bin = 2ull;
                       else if (u <= 4u) bin = 3ull;
                       else bin = 2ull + rc;
-                      if (!is_zero) {
+                      if (!pr.any4) {
+                        zr = 0ull;  // never read: no segment can have a run, so zero-run mode is not a candidate
+                      } else if (!is_zero) {
                         const uint32_t esc = 1u << (k + 3u < 24u ? k + 3u : 24u);
                         zr = 2ull + ((u > esc) ? 32ull : rc);
                       } else if (long_run) {

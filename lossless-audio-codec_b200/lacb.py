@@ -55,7 +55,7 @@ class BlockInfo(C.Structure):
 
 
 EXPORTS = ("lacb_create", "lacb_destroy", "lacb_last_error", "lacb_free", "lacb_device_count", "lacb_get_timing",
-           "lacb_encode", "lacb_encode_device", "lacb_decode", "lacb_decode_device", "lacb_encode_block",
+           "lacb_encode", "lacb_encode_to", "lacb_encode_device", "lacb_decode", "lacb_decode_device", "lacb_encode_block",
            "lacb_decode_block", "lacb_lpc_analyze", "lacb_last_block_info", "lacb_dev_malloc", "lacb_dev_free",
            "lacb_host_malloc", "lacb_host_free", "lacb_memcpy_h2d", "lacb_memcpy_d2h", "lacb_memcpy_d2d")
 
@@ -81,6 +81,8 @@ def load_library(path=None) -> C.CDLL:
     lib.lacb_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
     lib.lacb_encode.argtypes = [C.c_void_p, C.POINTER(EncParams), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                 C.POINTER(u8p), C.POINTER(C.c_uint64), u32p, C.POINTER(Err)]
+    lib.lacb_encode_to.argtypes = [C.c_void_p, C.POINTER(EncParams), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
+                                   C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p, C.POINTER(Err)]
     lib.lacb_encode_device.argtypes = [C.c_void_p, C.POINTER(EncParams), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
                                        C.POINTER(Err)]
@@ -216,6 +218,42 @@ class Codec:
             raise DecodeError(err.msg.decode())
         if rc != 0:
             raise RuntimeError(f"lacb_decode_device rc={rc}: {self.last_error()}")
+
+    # ---- host buffers owned by the caller (pinned memory = full PCIe speed) ------------
+    def pinned(self, nbytes: int) -> np.ndarray:
+        """uint8 array over page-locked host memory (lives as long as the context)."""
+        p = C.c_void_p()
+        if self.lib.lacb_host_malloc(self.h, nbytes, C.byref(p)) != 0:
+            raise RuntimeError("lacb_host_malloc: " + self.last_error())
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return np.ctypeslib.as_array(C.cast(p, u8p), shape=(max(nbytes, 1),))[:nbytes]
+
+    def encode_into(self, pcm_packed: np.ndarray, payload_buf: np.ndarray, block_bytes: np.ndarray, bit_depth,
+                    channels, stereo_mode, zero_run=True, partitioning=True) -> int:
+        """Packed PCM (host) -> payload written into payload_buf; returns the payload size."""
+        frames = pcm_packed.size // (channels * (bit_depth // 8))
+        prm = EncParams(0, bit_depth, channels, stereo_mode, int(zero_run), int(partitioning), 0)
+        n, err = C.c_uint64(), Err()
+        rc = self.lib.lacb_encode_to(self.h, C.byref(prm), LACB_PACKED_LE, pcm_packed.ctypes.data, None, frames,
+                                     payload_buf.ctypes.data, payload_buf.size, C.byref(n),
+                                     block_bytes.ctypes.data_as(u32p), C.byref(err))
+        if rc != 0:
+            raise RuntimeError(f"lacb_encode_to rc={rc} (needs {n.value} bytes): {self.last_error()}")
+        return n.value
+
+    def decode_into(self, payload: np.ndarray, block_sizes, block_bytes, bit_depth, channels, stereo_mode,
+                    out_packed: np.ndarray):
+        bs = np.ascontiguousarray(block_sizes, dtype=np.uint32)
+        bb = np.ascontiguousarray(block_bytes, dtype=np.uint32)
+        prm = DecParams(bit_depth, channels, stereo_mode)
+        err = Err()
+        rc = self.lib.lacb_decode(self.h, C.byref(prm), payload.ctypes.data, payload.size, bs.ctypes.data_as(u32p),
+                                  bb.ctypes.data_as(u32p), bs.size, LACB_PACKED_LE, out_packed.ctypes.data, None,
+                                  C.byref(err))
+        if rc == LACB_EDECODE:
+            raise DecodeError(err.msg.decode())
+        if rc != 0:
+            raise RuntimeError(f"lacb_decode rc={rc}: {self.last_error()}")
 
     # ---- block payloads ------------------------------------------------------------
     def encode_blocks(self, left, right=None, bit_depth=16, stereo_mode=0, zero_run=True, partitioning=True,
