@@ -37,7 +37,7 @@ struct lacb_ctx {
   cudaEvent_t ev[EV_COUNT] = {};
   DevBuf packed_in, planeL, planeR, flags, jobs, jobs_p, counts, acor, acor_p, lpcq, lpcq_p, recs, probe_bytes,
       blk_bytes, blk_off, misc, payload;
-  DevBuf d_payload, d_fs, d_size, d_boff, d_bytes, d_err, d_ms, d_L, d_R, d_packed, d_hdrs;
+  DevBuf d_payload, d_fs, d_size, d_boff, d_bytes, d_err, d_ms, d_L, d_R, d_packed, d_hdrs, d_order;
   void* pinned = nullptr;
   size_t pinned_cap = 0;
   lacb_block_info last_info{};
@@ -243,10 +243,13 @@ bool params_ok(const lacb_enc_params* p) {
 __global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, uint32_t n, int32_t* out, u64* result) {
   __shared__ uint32_t ring[kDriftWin];
   __shared__ ChanHdr hdr;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ ParseScratch sc;
+  const uint32_t lane = threadIdx.x & 31u;
   BitRd r;
   rd_init(r, data, size, data + padded);
-  bool ok = parse_channel_block(r, n, out, &hdr, ring);
+  bool ok = parse_channel_block(r, n, out, &hdr, ring, &sc, lane);
+  __syncwarp();
+  if (lane != 0u) return;
   if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef);
   result[0] = ok ? 1ull : 0ull;
   result[1] = ok ? rd_pos(r) - r.start : 0ull;
@@ -302,7 +305,7 @@ void lacb_destroy(lacb_ctx* ctx) {
                    &ctx->acor, &ctx->acor_p, &ctx->lpcq, &ctx->lpcq_p, &ctx->recs, &ctx->probe_bytes,
                    &ctx->blk_bytes, &ctx->blk_off, &ctx->misc, &ctx->payload, &ctx->d_payload, &ctx->d_fs,
                    &ctx->d_size, &ctx->d_boff, &ctx->d_bytes, &ctx->d_err, &ctx->d_ms, &ctx->d_L, &ctx->d_R,
-                   &ctx->d_packed, &ctx->d_hdrs};
+                   &ctx->d_packed, &ctx->d_hdrs, &ctx->d_order};
   for (DevBuf* b : all) release(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < EV_COUNT; ++i)
@@ -596,9 +599,14 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
               as<u64>(ctx->d_boff), as<uint32_t>(ctx->d_bytes), dL, dR, as<ChanHdr>(ctx->d_hdrs),
               as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms));
   CK(cudaEventRecord(ctx->ev[EV_LPC], st));
+  CKR(ensure(ctx, ctx->d_order, ((size_t)n_blocks * 2 + 8 * 32 + 1) * 4));
+  uint32_t* d_order = as<uint32_t>(ctx->d_order);
+  auto ko = k_restore_order;
+  LACB_LAUNCH(ko, 1, 1024, 0, st, cfg, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err), d_order + 1, d_order);
   auto kr = k_restore_blocks;
-  LACB_LAUNCH(kr, (n_blocks * prm->channels + 63u) / 64u, 64, 0, st, cfg, as<u64>(ctx->d_fs),
-              as<uint32_t>(ctx->d_size), dL, dR, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err));
+  LACB_LAUNCH(kr, (n_blocks * prm->channels + 8u * 32u + 63u) / 64u, 64, 0, st, cfg, as<u64>(ctx->d_fs),
+              as<uint32_t>(ctx->d_size), dL, dR, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err), d_order + 1,
+              d_order);
   auto km = k_merge_restore_errors;
   LACB_LAUNCH(km, (n_blocks + 255u) / 256u, 256, 0, st, cfg, as<uint32_t>(ctx->d_err));
   CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));

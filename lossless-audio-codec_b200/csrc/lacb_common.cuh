@@ -72,6 +72,19 @@ __device__ __forceinline__ uint32_t kbase_guess(u64 N, uint32_t c) {
   return g < 1 ? 1u : (uint32_t)g;
 }
 
+// Exact base k of the adaptive models without a division or a search:
+//   mean = floor(N / c), k = mean <= 1 ? 0 : min(31, bit_width(mean - 1))
+// With M = N - c >= c:  bit_width(mean - 1) = 1 + max{ s : (M >> s) >= c }, and that s is
+// bit_width(M) - bit_width(c), minus one when the shifted value falls short of c.
+__device__ __forceinline__ uint32_t kbase_clz(u64 N, uint32_t c) {
+  if (N < 2ull * c) return 0u;
+  const u64 M = N - c;
+  const uint32_t s0 = bitwidth64(M) - (32u - (uint32_t)__clz((int)c));
+  const uint32_t t = (uint32_t)(M >> s0);
+  const uint32_t kb = 1u + s0 - (t < c ? 1u : 0u);
+  return kb > 31u ? 31u : kb;
+}
+
 // rice_bits_for_unsigned, block/encoder.cpp:67-70
 __device__ __forceinline__ u64 rice_cost(uint32_t u, uint32_t k) {
   const uint32_t q = (k >= 31u) ? 0u : (u >> k);

@@ -152,8 +152,7 @@ __device__ __forceinline__ uint32_t ks_step(KState& st, uint32_t u, uint32_t* ri
   st.sum += u;
   const uint32_t c = ++st.count;
   const u64 N = st.sum + (c >> 1);
-  const uint32_t kb = kbase_from(N, c, st.kb);
-  st.kb = kb ? kb : 1u;
+  const uint32_t kb = kbase_clz(N, c);
   if (STATELESS) return kb;
   const uint32_t slot = (c - 1u) & (kDriftWin - 1u);
   st.win_sum += u;
@@ -242,9 +241,15 @@ __device__ __forceinline__ bool decode_segment(BitRd& r, uint32_t n, uint32_t k0
       if (!rd_rice(r, kZrRunK, &enc) || enc > 0xFFFFFFFFu - kZrMinRun) return false;
       const uint32_t run = enc + kZrMinRun;
       if (run > n - idx) return false;
-      for (uint32_t j = 0; j < run; ++j) {
-        res[idx++] = 0;
-        k = ks_step<STATELESS>(st, 0u, ring);
+      if (STATELESS) {  // count += run; k = adapt_k_stateless(sum, count)  (block/decoder.cpp:208-211)
+        for (uint32_t j = 0; j < run; ++j) res[idx++] = 0;
+        st.count += run;
+        k = kbase_clz(st.sum + (st.count >> 1), st.count);
+      } else {
+        for (uint32_t j = 0; j < run; ++j) {
+          res[idx++] = 0;
+          k = ks_step<STATELESS>(st, 0u, ring);
+        }
       }
       continue;
     }
@@ -275,65 +280,203 @@ struct ChanHdr {
 
 // Header + residual part of Block::Decoder::decode_into (block/decoder.cpp:64-512):
 // leaves the residual in `out` and the predictor description in `hdr`.
-__device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_t* out, ChanHdr* hdr, uint32_t* ring) {
-  if (n == 0u || n > kMaxBlock) return false;
-  const uint32_t type = rd_get(r, 8u);
-  const uint32_t order = rd_get(r, 8u);
-  if (rd_over(r)) return false;
-  if (type > 2u) return false;
-  if (type == PRED_LPC) {
-    if (order == 0u || order > 32u || order >= n) return false;
-  } else if (type == PRED_FIR) {
-    if (order != 2u) return false;
-  } else if (order > 4u) {
-    return false;
+// Per-warp scratch of the speculative token batches.
+struct ParseScratch {
+  uint32_t uval[32];
+  uint32_t wval[32];
+  u64 tpos[33];
+};
+
+// One token of a stateless adaptive segment (lane 0 only): value u, sample count w.
+//   MODE_RICE: Rice(k)                          block/decoder.cpp:126-136
+//   MODE_ZR  : tag 00 Rice(k) | 01 run | 10 raw block/decoder.cpp:138-257
+//   MODE_BIN : tag 00 | 01 s | 10 s | 11 Rice(k) block/decoder.cpp:259-294
+__device__ __forceinline__ bool parse_token(BitRd& r, uint32_t mode, uint32_t k, uint32_t* u, uint32_t* w) {
+  *w = 1u;
+  if (mode == MODE_RICE) return rd_rice(r, k, u);
+  const uint32_t tag = rd_get(r, 2u);
+  if (mode == MODE_BIN) {
+    if (tag == 0u) { *u = 0u; return true; }
+    if (tag == 3u) return rd_rice(r, k, u);
+    const uint32_t sign = rd_get(r, 1u);
+    *u = (tag == 1u) ? (sign ? 1u : 2u) : (sign ? 3u : 4u);
+    return true;
   }
-  hdr->type = (uint8_t)type;
-  hdr->order = (uint8_t)order;
-  if (type == PRED_LPC) {
-    for (uint32_t i = 1; i <= order; ++i) {
-      hdr->coef[i] = (int16_t)(uint16_t)rd_get(r, 16u);
-      if (rd_over(r)) return false;
+  if (tag > 2u) return false;
+  if (tag == 0u) return rd_rice(r, k, u);
+  if (tag == 2u) { *u = rd_get(r, 32u); return true; }
+  uint32_t enc;
+  if (!rd_rice(r, kZrRunK, &enc) || enc > 0xFFFFFFFFu - kZrMinRun) return false;
+  *u = 0u;
+  *w = enc + kZrMinRun;
+  return true;
+}
+
+// Warp-cooperative decode of one STATELESS adaptive segment (modes 0, 1, 2).
+//
+// The stateless k (block/encoder.cpp:72-77) depends only on (sum of u, sample count), so a
+// batch of tokens parsed by lane 0 under the assumption "k stays k" can be checked by the
+// whole warp with one prefix scan: lane i recomputes the k that follows token i; the first
+// lane whose k differs ends the valid prefix, the reader is rewound to the next token and
+// the batch restarts with the new k.  Valid tokens are committed with coalesced stores.
+// All lanes must call this; only lane 0's reader `r` is meaningful.
+__device__ __forceinline__ bool decode_segment_warp(BitRd& r, uint32_t n, uint32_t k0, uint32_t mode, int32_t* res,
+                                                    ParseScratch* sc, uint32_t lane) {
+  u64 sum = 0ull;
+  uint32_t count = 0u, idx = 0u, k = k0, B = 8u;
+  if (k0 > 31u) return false;
+  while (idx < n) {
+    uint32_t cnt = 0u, bad = 0u;
+    if (lane == 0u) {
+      const uint32_t left = n - idx;
+      uint32_t used = 0u;
+      while (cnt < B && used < left) {
+        sc->tpos[cnt] = rd_pos(r);
+        uint32_t u, w;
+        if (!parse_token(r, mode, k, &u, &w) || w > left - used || rd_over(r)) {
+          bad = 1u;
+          break;
+        }
+        sc->uval[cnt] = u;
+        sc->wval[cnt] = w;
+        used += w;
+        ++cnt;
+      }
+      if (!bad) sc->tpos[cnt] = rd_pos(r);
     }
+    cnt = __shfl_sync(kFull, cnt, 0);
+    bad = __shfl_sync(kFull, bad, 0);
+    __syncwarp();
+    if (cnt == 0u) return false;  // the very next token fails under the true k
+    const uint32_t u = lane < cnt ? sc->uval[lane] : 0u;
+    const uint32_t w = lane < cnt ? sc->wval[lane] : 0u;
+    u64 PU = u;
+    uint32_t PW = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 yu = __shfl_up_sync(kFull, PU, d);
+      const uint32_t yw = __shfl_up_sync(kFull, PW, d);
+      if (lane >= (uint32_t)d) {
+        PU += yu;
+        PW += yw;
+      }
+    }
+    const uint32_t c = count + PW;
+    const uint32_t knext = c ? kbase_clz(sum + PU + (c >> 1), c) : 0u;
+    const uint32_t mism = __ballot_sync(kFull, lane < cnt && knext != k);
+    const uint32_t valid = mism ? (uint32_t)__ffs((int)mism) : cnt;  // tokens [0, valid) used the right k
+    if (lane < valid) {
+      int32_t* dst = res + idx + (PW - w);
+      if (w == 1u) {
+        dst[0] = unzz32(u);
+      } else {
+        for (uint32_t j = 0; j < w; ++j) dst[j] = 0;
+      }
+    }
+    const uint32_t knew = __shfl_sync(kFull, knext, (int)valid - 1);
+    sum += __shfl_sync(kFull, PU, (int)valid - 1);
+    const uint32_t adv = __shfl_sync(kFull, PW, (int)valid - 1);
+    count += adv;
+    idx += adv;
+    const bool all_ok = (valid == cnt) && (knew == k);
+    if (bad && all_ok) return false;  // the failing token was parsed with the correct k
+    if (!all_ok || bad) {
+      if (lane == 0u) rd_seek(r, sc->tpos[valid]);
+      B = valid < 4u ? 4u : valid;
+    } else {
+      B = B * 2u > 32u ? 32u : B * 2u;
+    }
+    k = knew;
+    __syncwarp();
   }
-  const uint32_t control = rd_get(r, 8u);
-  if (rd_over(r)) return false;
-  if (control & 0x10u) return false;
-  const bool pflag = (control & 0x80u) != 0u;
-  const uint32_t p = control & 0x0Fu, cmode = (control >> 5) & 3u;
-  if (pflag && p == 0u) return false;
-  if (!pflag && p != 0u) return false;
-  if (p > kMaxPartOrder) return false;
-  if (p > 0u && (n >> p) < kMinPart) return false;
+  const uint32_t over = __shfl_sync(kFull, (uint32_t)rd_over(r), 0);
+  return over == 0u;
+}
+
+// Header + residual part of Block::Decoder::decode_into (block/decoder.cpp:64-512): leaves
+// the residual in `out` and the predictor description in `hdr`.  Warp collective: every
+// lane calls it, lane 0 owns the reader.
+__device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_t* out, ChanHdr* hdr, uint32_t* ring,
+                                                    ParseScratch* sc, uint32_t lane) {
+  if (n == 0u || n > kMaxBlock) return false;
+  uint32_t ok = 1u, p = 0u;
+  u64 table_pos = 0ull;
+  if (lane == 0u) {
+    ok = 0u;
+    do {
+      const uint32_t type = rd_get(r, 8u);
+      const uint32_t order = rd_get(r, 8u);
+      if (rd_over(r) || type > 2u) break;
+      if (type == PRED_LPC) {
+        if (order == 0u || order > 32u || order >= n) break;
+      } else if (type == PRED_FIR) {
+        if (order != 2u) break;
+      } else if (order > 4u) {
+        break;
+      }
+      hdr->type = (uint8_t)type;
+      hdr->order = (uint8_t)order;
+      bool bad = false;
+      if (type == PRED_LPC) {
+        for (uint32_t i = 1; i <= order && !bad; ++i) {
+          hdr->coef[i] = (int16_t)(uint16_t)rd_get(r, 16u);
+          bad = rd_over(r);
+        }
+      }
+      if (bad) break;
+      const uint32_t control = rd_get(r, 8u);
+      if (rd_over(r) || (control & 0x10u)) break;
+      const bool pflag = (control & 0x80u) != 0u;
+      p = control & 0x0Fu;
+      const uint32_t cmode = (control >> 5) & 3u;
+      if ((pflag && p == 0u) || (!pflag && p != 0u) || p > kMaxPartOrder) break;
+      if (p > 0u && (n >> p) < kMinPart) break;
+      // the partition table sits in front of the tokens (block/decoder.cpp:447-455): remember
+      // where it starts and read each entry when its segment comes up
+      table_pos = rd_pos(r);
+      const u64 tokens_pos = table_pos + 7ull * (1u << p);
+      if (tokens_pos > r.end) break;
+      if ((rd_get(r, 7u) >> 5) != cmode) break;
+      rd_seek(r, tokens_pos);
+      ok = 1u;
+    } while (false);
+  }
+  ok = __shfl_sync(kFull, ok, 0);
+  p = __shfl_sync(kFull, p, 0);
+  if (!ok) return false;
   const uint32_t cnt = 1u << p;
-  // the partition table sits in front of the tokens (block/decoder.cpp:447-455): remember
-  // where it starts and read each entry when its segment comes up
-  const u64 table_pos = rd_pos(r);
-  const u64 tokens_pos = table_pos + 7ull * cnt;
-  if (tokens_pos > r.end) return false;
-  if ((rd_get(r, 7u) >> 5) != cmode) return false;
-  rd_seek(r, tokens_pos);
   uint32_t off = 0u;
   for (uint32_t i = 0; i < cnt; ++i) {
-    uint32_t mk;
-    {
+    uint32_t mk = 0u;
+    if (lane == 0u) {
       BitRd t = r;  // table entry i (the reader is a handful of registers)
       rd_seek(t, table_pos + 7ull * i);
       mk = rd_get(t, 7u);
     }
+    mk = __shfl_sync(kFull, mk, 0);
     const uint32_t len = part_len(n, p, i);
-    const bool ok = p ? decode_segment<true>(r, len, mk & 31u, mk >> 5, out + off, ring)
-                      : decode_segment<false>(r, len, mk & 31u, mk >> 5, out + off, ring);
+    const uint32_t mode = mk >> 5, k0 = mk & 31u;
+    if (p && mode != MODE_STATIC) {
+      ok = decode_segment_warp(r, len, k0, mode, out + off, sc, lane) ? 1u : 0u;
+    } else {
+      if (lane == 0u)
+        ok = (p ? decode_segment<true>(r, len, k0, mode, out + off, ring)
+                : decode_segment<false>(r, len, k0, mode, out + off, ring)) ? 1u : 0u;
+      ok = __shfl_sync(kFull, ok, 0);
+    }
     if (!ok) return false;
     off += len;
   }
-  // consume_zero_padding_to_byte (bit_reader.hpp:180-185)
-  const uint32_t padn = (uint32_t)((8ull - ((rd_pos(r) - r.start) & 7ull)) & 7ull);
-  if (padn) {
-    if (rd_get(r, padn) != 0u) return false;
-    if (rd_over(r)) return false;
+  if (lane == 0u) {
+    // consume_zero_padding_to_byte (bit_reader.hpp:180-185)
+    const uint32_t padn = (uint32_t)((8ull - ((rd_pos(r) - r.start) & 7ull)) & 7ull);
+    if (padn) {
+      if (rd_get(r, padn) != 0u) ok = 0u;
+      if (rd_over(r)) ok = 0u;
+    }
   }
-  return true;
+  ok = __shfl_sync(kFull, ok, 0);
+  return ok != 0u;
 }
 
 // Runs step(i, value&) over x[0..n) in order, 8 samples at a time: the next chunk's loads
@@ -459,10 +602,12 @@ __global__ void __launch_bounds__(32 * kParseWarps, 32) k_parse_blocks(
     const uint32_t* __restrict__ blk_size, const u64* __restrict__ blk_boff, const uint32_t* __restrict__ blk_bytes,
     int32_t* L, int32_t* R, ChanHdr* hdrs, uint32_t* blk_err, uint8_t* blk_ms) {
   __shared__ uint32_t rings[kParseWarps][kDriftWin];
+  __shared__ ParseScratch scratch[kParseWarps];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t b = blockIdx.x * kParseWarps + warp;
-  if (b >= cfg.n_blocks || lane != 0u) return;
+  if (b >= cfg.n_blocks) return;
   uint32_t* ring = rings[warp];
+  ParseScratch* sc = &scratch[warp];
   const uint8_t* begin = payload + blk_boff[b];
   BitRd r;
   rd_init(r, begin, blk_bytes[b], payload + payload_bytes);
@@ -470,31 +615,77 @@ __global__ void __launch_bounds__(32 * kParseWarps, 32) k_parse_blocks(
   uint32_t err = DERR_OK;
   uint32_t ms = 0u;
   if (cfg.channels == 2u && cfg.stereo_mode == 2u) {
-    const uint32_t flag = rd_get(r, 8u);
+    const uint32_t flag = rd_get(r, 8u);  // every lane reads the same byte
     if (rd_over(r) || flag > 1u) err = DERR_FLAG;
     ms = flag == 1u;
   } else if (cfg.channels == 2u && cfg.stereo_mode == 1u) {
     ms = 1u;
   }
-  if (!err && !parse_channel_block(r, n, L + blk_fs[b], hdrs + (size_t)b * 2u, ring)) err = DERR_PRIMARY;
-  if (!err && cfg.channels == 2u && !parse_channel_block(r, n, R + blk_fs[b], hdrs + (size_t)b * 2u + 1u, ring))
+  if (!err && !parse_channel_block(r, n, L + blk_fs[b], hdrs + (size_t)b * 2u, ring, sc, lane)) err = DERR_PRIMARY;
+  if (!err && cfg.channels == 2u &&
+      !parse_channel_block(r, n, R + blk_fs[b], hdrs + (size_t)b * 2u + 1u, ring, sc, lane))
     err = DERR_SECONDARY;
-  if (!err && rd_pos(r) != r.end) err = DERR_TRAILING;  // checked after reconstruction in the reference
-  blk_err[b] = err;
-  blk_ms[b] = (uint8_t)ms;
+  if (lane == 0u) {
+    if (!err && rd_pos(r) != r.end) err = DERR_TRAILING;  // checked after reconstruction in the reference
+    blk_err[b] = err;
+    blk_ms[b] = (uint8_t)ms;
+  }
 }
 
 // K12b: one thread per channel-block.  A reconstruction overflow is a primary / secondary
 // channel failure (Block::Decoder::decode_into returns false), which outranks the
 // trailing-payload error recorded by the parser.
+//
+// Channel-blocks are first grouped by predictor kind (fixed order 1..4, FIR, LPC <= 12,
+// LPC > 12), each group padded to a warp boundary, so the 32 lanes of a restore warp run
+// the same counted loop instead of serialising three different recurrences.
+__device__ __forceinline__ uint32_t restore_key(const ChanHdr& h, uint32_t err, uint32_t ch) {
+  if (err == DERR_FLAG || err == DERR_PRIMARY || (err == DERR_SECONDARY && ch == 1u)) return 0u;
+  if (h.type == PRED_FIXED) return h.order;  // 0: nothing to do
+  if (h.type == PRED_FIR) return 5u;
+  return h.order <= 12u ? 6u : 7u;
+}
+__global__ void __launch_bounds__(1024) k_restore_order(DecCfg cfg, const ChanHdr* __restrict__ hdrs,
+                                                        const uint32_t* __restrict__ blk_err, uint32_t* order,
+                                                        uint32_t* n_order) {
+  __shared__ uint32_t cnt[8], cur[8];
+  const uint32_t tid = threadIdx.x, nj = cfg.n_blocks * cfg.channels;
+  if (tid < 8u) cnt[tid] = 0u;
+  __syncthreads();
+  for (uint32_t j = tid; j < nj; j += blockDim.x) {
+    const uint32_t b = j / cfg.channels, ch = j - b * cfg.channels;
+    const uint32_t key = restore_key(hdrs[(size_t)b * 2u + ch], blk_err[b] & 0xFFu, ch);
+    if (key) atomicAdd(&cnt[key], 1u);
+  }
+  __syncthreads();
+  if (tid == 0u) {
+    uint32_t pos = 0u;
+    for (uint32_t k = 1; k < 8u; ++k) {
+      cur[k] = pos;
+      pos += (cnt[k] + 31u) & ~31u;
+    }
+    *n_order = pos;
+  }
+  __syncthreads();
+  const uint32_t total = *n_order;
+  for (uint32_t i = tid; i < total; i += blockDim.x) order[i] = 0xFFFFFFFFu;
+  __syncthreads();
+  for (uint32_t j = tid; j < nj; j += blockDim.x) {
+    const uint32_t b = j / cfg.channels, ch = j - b * cfg.channels;
+    const uint32_t key = restore_key(hdrs[(size_t)b * 2u + ch], blk_err[b] & 0xFFu, ch);
+    if (key) order[atomicAdd(&cur[key], 1u)] = j;
+  }
+}
 __global__ void __launch_bounds__(64) k_restore_blocks(DecCfg cfg, const u64* __restrict__ blk_fs,
                                                        const uint32_t* __restrict__ blk_size, int32_t* L, int32_t* R,
-                                                       const ChanHdr* __restrict__ hdrs, uint32_t* blk_err) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cfg.n_blocks * cfg.channels) return;
+                                                       const ChanHdr* __restrict__ hdrs, uint32_t* blk_err,
+                                                       const uint32_t* __restrict__ order,
+                                                       const uint32_t* __restrict__ n_order) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_order) return;
+  const uint32_t j = order[i];
+  if (j == 0xFFFFFFFFu) return;
   const uint32_t b = j / cfg.channels, ch = j - b * cfg.channels;
-  const uint32_t e = blk_err[b] & 0xFFu;
-  if (e == DERR_FLAG || e == DERR_PRIMARY || (e == DERR_SECONDARY && ch == 1u)) return;
   const ChanHdr* h = hdrs + (size_t)b * 2u + ch;
   int32_t* x = (ch ? R : L) + blk_fs[b];
   if (!restore_block(x, blk_size[b], h->type, h->order, h->coef)) atomicOr(&blk_err[b], 0x100u << ch);

@@ -364,19 +364,6 @@ __device__ __forceinline__ SegGeom seg_geom(uint32_t g0, uint32_t n, uint32_t p)
   return g;
 }
 
-// Exact base k of the adaptive models without a division or a search:
-//   mean = floor(N / c), k = mean <= 1 ? 0 : min(31, bit_width(mean - 1))
-// With M = N - c >= c:  bit_width(mean - 1) = 1 + max{ s : (M >> s) >= c }, and that s is
-// bit_width(M) - bit_width(c), minus one when the shifted value falls short of c.
-__device__ __forceinline__ uint32_t kbase_clz(u64 N, uint32_t c) {
-  if (N < 2ull * c) return 0u;
-  const u64 M = N - c;
-  const uint32_t s0 = bitwidth64(M) - (32u - (uint32_t)__clz((int)c));
-  const uint32_t t = (uint32_t)(M >> s0);
-  const uint32_t kb = 1u + s0 - (t < c ? 1u : 0u);
-  return kb > 31u ? 31u : kb;
-}
-
 // k series of one level.  On return the K plane holds, for every sample i, the Rice
 // parameter the model yields AFTER consuming sample i (the k used for sample i+1 unless
 // that sample starts a segment).
