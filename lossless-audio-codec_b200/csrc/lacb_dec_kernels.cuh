@@ -45,21 +45,24 @@ struct BitRd {
   u64 w;
   uint32_t avail;   // valid bits in w
   uint32_t wi;      // index of the word held in nextw
-  uint32_t nextw;
+  uint32_t nextw;   // raw (little-endian) prefetched word
   uint32_t last_word;
   u64 start, end;
 };
-__device__ __forceinline__ uint32_t rd_word(const BitRd& r, uint32_t i) {
+__device__ __forceinline__ uint32_t rd_word_raw(const BitRd& r, uint32_t i) {
   i = i > r.last_word ? r.last_word : i;
-  return __byte_perm(__ldg(r.base + i), 0u, 0x0123);
+  return __ldg(r.base + i);
 }
+__device__ __forceinline__ uint32_t rd_word(const BitRd& r, uint32_t i) { return __byte_perm(rd_word_raw(r, i), 0u, 0x0123); }
 __device__ __forceinline__ u64 rd_pos(const BitRd& r) { return (u64)r.wi * 32ull - r.avail; }
 __device__ __forceinline__ void rd_refill(BitRd& r) {
   if (r.avail <= 32u) {
-    r.w |= (u64)r.nextw << (32u - r.avail);
+    // nextw holds the little-endian word as loaded: swapping it here, one refill after the
+    // load was issued, keeps the load latency off the dependent chain
+    r.w |= (u64)__byte_perm(r.nextw, 0u, 0x0123) << (32u - r.avail);
     r.avail += 32u;
     r.wi += 1u;
-    r.nextw = rd_word(r, r.wi);
+    r.nextw = rd_word_raw(r, r.wi);
   }
 }
 __device__ __forceinline__ void rd_seek(BitRd& r, u64 pos) {
@@ -69,7 +72,7 @@ __device__ __forceinline__ void rd_seek(BitRd& r, u64 pos) {
   r.w = (u64)rd_word(r, w0) << (32u + sh);
   r.avail = 32u - sh;
   r.wi = w0 + 1u;
-  r.nextw = rd_word(r, r.wi);
+  r.nextw = rd_word_raw(r, r.wi);
   rd_refill(r);
 }
 __device__ __forceinline__ void rd_init(BitRd& r, const uint8_t* begin, u64 nbytes, const uint8_t* buf_end) {
@@ -284,7 +287,8 @@ struct ChanHdr {
 struct ParseScratch {
   uint32_t uval[32];
   uint32_t wval[32];
-  u64 tpos[33];
+  uint32_t twi[33];   // reader position before token t: word index ...
+  uint32_t tav[33];   // ... and valid bits in the window (pos = wi * 32 - avail)
 };
 
 // One token of a stateless adaptive segment (lane 0 only): value u, sample count w.
@@ -331,9 +335,10 @@ __device__ __forceinline__ bool decode_segment_warp(BitRd& r, uint32_t n, uint32
       const uint32_t left = n - idx;
       uint32_t used = 0u;
       while (cnt < B && used < left) {
-        sc->tpos[cnt] = rd_pos(r);
+        sc->twi[cnt] = r.wi;
+        sc->tav[cnt] = r.avail;
         uint32_t u, w;
-        if (!parse_token(r, mode, k, &u, &w) || w > left - used || rd_over(r)) {
+        if (!parse_token(r, mode, k, &u, &w) || w > left - used) {
           bad = 1u;
           break;
         }
@@ -342,7 +347,14 @@ __device__ __forceinline__ bool decode_segment_warp(BitRd& r, uint32_t n, uint32
         used += w;
         ++cnt;
       }
-      if (!bad) sc->tpos[cnt] = rd_pos(r);
+      if (!bad) {
+        sc->twi[cnt] = r.wi;
+        sc->tav[cnt] = r.avail;
+        if (rd_over(r)) {  // ran past the block: the last token cannot stand (checked once per batch)
+          bad = 1u;
+          --cnt;
+        }
+      }
     }
     cnt = __shfl_sync(kFull, cnt, 0);
     bad = __shfl_sync(kFull, bad, 0);
@@ -381,7 +393,7 @@ __device__ __forceinline__ bool decode_segment_warp(BitRd& r, uint32_t n, uint32
     const bool all_ok = (valid == cnt) && (knew == k);
     if (bad && all_ok) return false;  // the failing token was parsed with the correct k
     if (!all_ok || bad) {
-      if (lane == 0u) rd_seek(r, sc->tpos[valid]);
+      if (lane == 0u) rd_seek(r, (u64)sc->twi[valid] * 32ull - sc->tav[valid]);
       B = valid < 4u ? 4u : valid;
     } else {
       B = B * 2u > 32u ? 32u : B * 2u;
