@@ -441,7 +441,11 @@ __global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const ui
     Prep<NT, E> pr;
     prepare<NT, E, true>(sm, r, n, pr);
 
+#ifdef LACB_X_NOLEVELS
+    const uint32_t max_p = 0u;
+#else
     const uint32_t max_p = (cfg.partitioning && n >= kMinPart) ? max_partition_order(n) : 0u;
+#endif
     // per-segment initial k, static k / bits and prefix of u, all levels at once
     for (uint32_t sid = tid; sid < (2u << max_p) - 1u; sid += NT) {
       const uint32_t p = 31u - (uint32_t)__clz((int)(sid + 1u));

@@ -284,7 +284,12 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   pr.lnz_ex = block_excl_max_i32<NT>(lastnz, reinterpret_cast<int32_t*>(sm.Scr()));
 
   PlaneCounts pc;
+#ifdef LACB_X_NOPREP
+  for (int w = 0; w < 8; ++w) pc.w[w] = V[w % 5];
+  if (!FULL) { __syncthreads(); pr.any4 = 0u; return; }
+#else
   planes_from_sliced(V, pc);
+#endif
   if (FULL) {
     PlaneCounts* Cp = sm.Cpre();
 #pragma unroll
@@ -398,6 +403,9 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
       const u64 lo = (1ull << (kb0 - 1u)) + 1ull, hi = (1ull << kb0) + 1ull;
       uniform = (N_first >= lo * c_last) && (kb0 == 31u || N_last < hi * c_first);
     }
+#ifdef LACB_X_NOKSER
+    uniform = true;
+#endif
     if (uniform) {
 #pragma unroll
       for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = kb0 * 0x01010101u;
@@ -449,6 +457,9 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
   const uint32_t part = ((int)tid - D >= 0) ? Flg[tid - D] : 0u;
   const int tt = (int)tid - DW;
   u64 wprev = tt >= 0 ? sm.Pthr()[tt] : 0ull;  // becomes the inclusive prefix at item j of thread tt
+#ifdef LACB_X_NOBIAS
+  return;
+#endif
   {
     // Cheap proof that every bias in this chunk is 0 (then the k series is the base series):
     //  * micro window: even counting every flag of the 7 threads it can touch, neither
@@ -628,6 +639,9 @@ template <int NT, int E, typename F>
 __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                            const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
   if (threadIdx.x * E >= n) return;
+#ifdef LACB_X_NOWALK
+  return;
+#endif
   if (pr.any4) {
     if (sg.fast) walk_thread<NT, E, true, true>(sm, pr, n, sg, kinitA, kinitB, f);
     else walk_thread<NT, E, false, true>(sm, pr, n, sg, kinitA, kinitB, f);
