@@ -333,7 +333,7 @@ __device__ __forceinline__ bool compute_residual(const int32_t (&x)[E + 12], uin
 }
 
 template <int NT, int E, bool PROBE>
-__global__ void __launch_bounds__(NT) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
+__global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
                                                 const LpcQ* lpcq, ChanRec* recs, uint32_t* probe_bytes) {
   LACB_DYN_SMEM(unsigned char, smraw);
   ASmem<NT, E> sm{smraw};

@@ -34,7 +34,12 @@ def synth_packed(seed, frames, depth, channels):
     return out
 
 
+ONLY = ""
+
+
 def run_case(cd, name, seed, seconds, rate, depth, channels, mode, reps=3, decode=True):
+    if ONLY and ONLY not in name:
+        return None
     frames = rate * seconds
     pk = synth_packed(seed, frames, depth, channels)
     nb = (frames + 16383) // 16384
@@ -79,8 +84,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="1/10 durations")
     ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="", help="run only the configs whose name contains this text")
     args = ap.parse_args()
     q = 10 if args.quick else 1
+    global ONLY
+    ONLY = args.only
     cd = load_package().Codec(0)
     lines = []
     t0 = time.time()
@@ -95,7 +103,7 @@ def main():
                                   reps=2))
     print(f"# total {time.time() - t0:.1f} s", flush=True)
     if args.out:
-        Path(args.out).write_text("\n".join(json.dumps(x) for x in lines) + "\n")
+        Path(args.out).write_text("\n".join(json.dumps(x) for x in lines if x) + "\n")
 
 
 if __name__ == "__main__":
