@@ -121,7 +121,9 @@ int lacb_memcpy_d2h(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 
 /* Decode n_blocks blocks whose concatenated payloads start at `payload` (HOST memory).
- * block_sizes / block_bytes come from the v3 block table.  Output (HOST memory):
+ * block_sizes / block_bytes come from the v3 block table; block_bytes == NULL selects the
+ * legacy v2 layout (no per-block byte sizes: the payload is walked as one serial chain,
+ * src/codec/lac/decoder.cpp:209-218).  Output (HOST memory):
  *   LACB_PLANAR_I32 -> out_a / out_b int32 planes (out_b NULL for mono)
  *   LACB_PACKED_LE  -> out_a = interleaved little-endian bit_depth/8-byte samples
  */

@@ -558,6 +558,7 @@ int lacb_lpc_analyze(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int order, i
 static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* d_payload, uint64_t payload_bytes,
                          const uint32_t* block_sizes, const uint32_t* block_bytes, uint32_t n_blocks, int32_t* dL,
                          int32_t* dR, uint8_t* d_packed, lacb_err* err) {
+  const bool serial = block_bytes == nullptr;  // v2 stream: one chain, no per-block byte sizes
   cudaStream_t st = ctx->stream;
   // tables: first sample and byte offset of every block (host prefix sums, O(n_blocks))
   const size_t tb = (size_t)n_blocks * (8 + 4 + 8 + 4);
@@ -571,9 +572,9 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
     h_fs[b] = fs;
     h_boff[b] = bo;
     h_size[b] = block_sizes[b];
-    h_bytes[b] = block_bytes[b];
+    h_bytes[b] = serial ? 0u : block_bytes[b];
     fs += block_sizes[b];
-    bo += block_bytes[b];
+    bo += h_bytes[b];
   }
   if (bo > payload_bytes) {
     ctx->err = "compressed block sizes exceed frame payload";
@@ -593,11 +594,19 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   CK(cudaEventRecord(ctx->ev[EV_H2D], st));
   DecCfg cfg{prm->channels, prm->stereo_mode, prm->bit_depth, n_blocks};
   CKR(ensure(ctx, ctx->d_hdrs, (size_t)n_blocks * 2 * sizeof(ChanHdr)));
-  auto kp = k_parse_blocks;
-  LACB_LAUNCH(kp, (n_blocks + kParseWarps - 1) / kParseWarps, 32 * kParseWarps, 0, st, cfg, d_payload,
-              (u64)((payload_bytes + 15ull) & ~15ull), as<u64>(ctx->d_fs), as<uint32_t>(ctx->d_size),
-              as<u64>(ctx->d_boff), as<uint32_t>(ctx->d_bytes), dL, dR, as<ChanHdr>(ctx->d_hdrs),
-              as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms));
+  if (serial) {
+    CKR(ensure(ctx, ctx->misc, 64));
+    auto ks = k_parse_serial;
+    LACB_LAUNCH(ks, 1, 32, 0, st, cfg, d_payload, (u64)payload_bytes, (u64)((payload_bytes + 15ull) & ~15ull),
+                as<u64>(ctx->d_fs), as<uint32_t>(ctx->d_size), dL, dR, as<ChanHdr>(ctx->d_hdrs),
+                as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms), as<uint32_t>(ctx->misc));
+  } else {
+    auto kp = k_parse_blocks;
+    LACB_LAUNCH(kp, (n_blocks + kParseWarps - 1) / kParseWarps, 32 * kParseWarps, 0, st, cfg, d_payload,
+                (u64)((payload_bytes + 15ull) & ~15ull), as<u64>(ctx->d_fs), as<uint32_t>(ctx->d_size),
+                as<u64>(ctx->d_boff), as<uint32_t>(ctx->d_bytes), dL, dR, as<ChanHdr>(ctx->d_hdrs),
+                as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms));
+  }
   CK(cudaEventRecord(ctx->ev[EV_LPC], st));
   CKR(ensure(ctx, ctx->d_order, ((size_t)n_blocks * 2 + 8 * 32 + 1) * 4));
   uint32_t* d_order = as<uint32_t>(ctx->d_order);
@@ -617,11 +626,16 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   return 0;
 }
 
-static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err) {
+static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err, bool serial = false) {
   std::vector<uint32_t> herr(n_blocks);
+  uint32_t info[2] = {n_blocks, 0u};
   CK(cudaMemcpyAsync(herr.data(), ctx->d_err.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (serial) CK(cudaMemcpyAsync(info, ctx->misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaGetLastError());
+  if (serial) {  // blocks after the first failure were never parsed
+    for (uint32_t b = info[0] + 1u; b < n_blocks; ++b) herr[b] = DERR_OK;
+  }
   for (uint32_t b = 0; b < n_blocks; ++b) {
     if (herr[b] == DERR_OK) continue;
     char msg[160];
@@ -634,6 +648,11 @@ static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err) 
     }
     ctx->err = msg;
     set_err(err, LACB_EDECODE, b, herr[b], msg);
+    return LACB_EDECODE;
+  }
+  if (serial && info[1]) {
+    ctx->err = "[decode-error] trailing frame payload";
+    set_err(err, LACB_EDECODE, n_blocks, DERR_TRAILING, "[decode-error] trailing frame payload");
     return LACB_EDECODE;
   }
   return 0;
@@ -686,7 +705,7 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
                 const uint32_t* block_sizes, const uint32_t* block_bytes, uint32_t n_blocks, int layout, void* out_a,
                 void* out_b, lacb_err* err) {
   if (!ctx) return LACB_EINVAL;
-  if (!dec_params_ok(prm) || !payload || !block_sizes || !block_bytes || n_blocks == 0 || !out_a ||
+  if (!dec_params_ok(prm) || !payload || !block_sizes || n_blocks == 0 || !out_a ||
       (layout == LACB_PLANAR_I32 && prm->channels == 2 && !out_b) ||
       (layout != LACB_PLANAR_I32 && layout != LACB_PACKED_LE)) {
     ctx->err = "invalid decode arguments";
@@ -713,7 +732,7 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
   CKR(decode_common(ctx, prm, as<uint8_t>(ctx->d_payload), payload_bytes, block_sizes, block_bytes, n_blocks,
                     as<int32_t>(ctx->d_L), as<int32_t>(ctx->d_R),
                     layout == LACB_PACKED_LE ? as<uint8_t>(ctx->d_packed) : nullptr, err));
-  const int rc = decode_check_errors(ctx, n_blocks, err);
+  const int rc = decode_check_errors(ctx, n_blocks, err, block_bytes == nullptr);
   if (rc != 0) return rc;
   if (layout == LACB_PACKED_LE) {
     CK(cudaMemcpyAsync(out_a, ctx->d_packed.p, frames * prm->channels * bps, cudaMemcpyDeviceToHost, st));

@@ -644,6 +644,54 @@ __global__ void __launch_bounds__(32 * kParseWarps, 32) k_parse_blocks(
   }
 }
 
+// Legacy v2 streams (lac/decoder.cpp:209-218): no per-block byte sizes, so the whole frame
+// payload is one bit-serial chain.  A single warp walks the blocks in order with the same
+// block parser; the first failing block stops the walk.  info[0] = blocks parsed OK,
+// info[1] = 1 when payload bits remain after the last block ("trailing frame payload").
+__global__ void __launch_bounds__(32) k_parse_serial(DecCfg cfg, const uint8_t* __restrict__ payload, u64 payload_bytes,
+                                                     u64 padded_bytes, const u64* __restrict__ blk_fs,
+                                                     const uint32_t* __restrict__ blk_size, int32_t* L, int32_t* R,
+                                                     ChanHdr* hdrs, uint32_t* blk_err, uint8_t* blk_ms, uint32_t* info) {
+  __shared__ uint32_t ring[kDriftWin];
+  __shared__ ParseScratch sc;
+  const uint32_t lane = threadIdx.x & 31u;
+  BitRd r;
+  rd_init(r, payload, payload_bytes, payload + padded_bytes);
+  uint32_t done = 0u;
+  for (uint32_t b = 0; b < cfg.n_blocks; ++b) {
+    uint32_t err = DERR_OK, ms = 0u;
+    if (cfg.channels == 2u && cfg.stereo_mode == 2u) {
+      uint32_t flag = 0u, over = 0u;
+      if (lane == 0u) {
+        flag = rd_get(r, 8u);
+        over = rd_over(r);
+      }
+      flag = __shfl_sync(kFull, flag, 0);
+      over = __shfl_sync(kFull, over, 0);
+      if (over || flag > 1u) err = DERR_FLAG;
+      ms = flag == 1u;
+    } else if (cfg.channels == 2u && cfg.stereo_mode == 1u) {
+      ms = 1u;
+    }
+    const uint32_t n = blk_size[b];
+    if (!err && !parse_channel_block(r, n, L + blk_fs[b], hdrs + (size_t)b * 2u, ring, &sc, lane)) err = DERR_PRIMARY;
+    if (!err && cfg.channels == 2u &&
+        !parse_channel_block(r, n, R + blk_fs[b], hdrs + (size_t)b * 2u + 1u, ring, &sc, lane))
+      err = DERR_SECONDARY;
+    if (lane == 0u) {
+      blk_err[b] = err;
+      blk_ms[b] = (uint8_t)ms;
+    }
+    if (err) break;
+    ++done;
+  }
+  if (lane == 0u) {
+    for (uint32_t b = done + 1u; b < cfg.n_blocks; ++b) blk_err[b] = DERR_PRIMARY;  // never reached; keeps them out of later stages
+    info[0] = done;
+    info[1] = (done == cfg.n_blocks && rd_pos(r) != r.end) ? 1u : 0u;
+  }
+}
+
 // K12b: one thread per channel-block.  A reconstruction overflow is a primary / secondary
 // channel failure (Block::Decoder::decode_into returns false), which outranks the
 // trailing-payload error recorded by the parser.

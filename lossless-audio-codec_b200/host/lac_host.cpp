@@ -132,31 +132,34 @@ ParsedFrame parse_frame(const uint8_t* data, size_t size) {
   if (data == nullptr || size == 0) throw_decode_error("empty input");
   size_t hb = 0;
   if (!FrameHeader::parse(data, size, pf.hdr, hb)) throw_decode_error("invalid frame header");
-  if (pf.hdr.version < 3)
-    throw_decode_error("serial v2 streams are not supported by the GPU path");
+  const bool v3 = pf.hdr.version >= 3;
   const uint8_t* body = data + hb;
   const uint64_t body_bytes = size - hb;
   if (body_bytes < 4) throw_decode_error("invalid block count");
   const uint32_t nb = be32(body);
   if (nb == 0 || nb > kMaxBlockCount) throw_decode_error("invalid block count");
-  if (nb > ((body_bytes - 4) * 8u) / 64u) throw_decode_error("truncated block size table");
+  const uint32_t words = v3 ? 2u : 1u;  // v2 tables carry sample counts only
+  if (nb > ((body_bytes - 4) * 8u) / (32u * words)) throw_decode_error("truncated block size table");
   pf.sizes.resize(nb);
-  pf.bytes.resize(nb);
+  pf.bytes.resize(v3 ? nb : 0);
   uint64_t total = 0, total_bytes = 0;
   for (uint32_t i = 0; i < nb; ++i) {
-    const uint32_t s = be32(body + 4 + 8ull * i), b = be32(body + 8 + 8ull * i);
+    const uint32_t s = be32(body + 4 + 4ull * words * i);
     if (s == 0 || s > kMaxBlock || (i + 1 < nb && s < kMinNonFinalBlock)) throw_decode_error("invalid block size");
     total += s;
     if (total > kMaxTotalSamples) throw_decode_error("total samples exceed maximum");
-    if (b == 0) throw_decode_error("invalid compressed block size");
-    total_bytes += b;
-    if (total_bytes > body_bytes) throw_decode_error("compressed block sizes exceed frame payload");
     pf.sizes[i] = s;
-    pf.bytes[i] = b;
+    if (v3) {
+      const uint32_t b = be32(body + 8 + 8ull * i);
+      if (b == 0) throw_decode_error("invalid compressed block size");
+      total_bytes += b;
+      if (total_bytes > body_bytes) throw_decode_error("compressed block sizes exceed frame payload");
+      pf.bytes[i] = b;
+    }
   }
   pf.frames = total;
-  pf.payload = body + 4 + 8ull * nb;
-  pf.payload_bytes = body_bytes - 4 - 8ull * nb;
+  pf.payload = body + 4 + 4ull * words * nb;
+  pf.payload_bytes = body_bytes - 4 - 4ull * words * nb;
   return pf;
 }
 
@@ -167,7 +170,8 @@ void check_decode_limits(const ParsedFrame& pf, bool planes) {
     throw_decode_error("decoded PCM allocation exceeds maximum");
   const uint64_t wav = pf.frames * pf.hdr.channels * (pf.hdr.bit_depth / 8u);
   if (36u + wav + (wav & 1u) > 0xFFFFFFFFull) throw_decode_error("decoded WAV data exceeds RIFF limit");
-  if (total_bytes != pf.payload_bytes) throw_decode_error("compressed block sizes do not match frame payload");
+  if (pf.hdr.version >= 3 && total_bytes != pf.payload_bytes)
+    throw_decode_error("compressed block sizes do not match frame payload");
 }
 
 void run_decode(const ParsedFrame& pf, int layout, void* out_a, void* out_b, LAC::ThreadCollector* collector) {
@@ -176,7 +180,9 @@ void run_decode(const ParsedFrame& pf, int layout, void* out_a, void* out_b, LAC
   lacb_ctx* ctx = ctx_for(0);
   std::lock_guard<std::mutex> lock(g_slots[0].mu);
   if (collector) collector->record(std::this_thread::get_id());
-  const int rc = lacb_decode(ctx, &prm, pf.payload, pf.payload_bytes, pf.sizes.data(), pf.bytes.data(),
+  // v2 streams have no per-block byte sizes: NULL selects the serial walk
+  const int rc = lacb_decode(ctx, &prm, pf.payload, pf.payload_bytes, pf.sizes.data(),
+                             pf.bytes.empty() ? nullptr : pf.bytes.data(),
                              (uint32_t)pf.sizes.size(), layout, out_a, out_b, &err);
   if (rc == LACB_EDECODE) throw std::runtime_error(err.msg);
   if (rc != 0) throw std::runtime_error(std::string("LAC B200 backend: ") + lacb_last_error(ctx));

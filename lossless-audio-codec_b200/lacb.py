@@ -290,21 +290,21 @@ class Codec:
     def decode_blocks(self, payload, block_sizes, block_bytes, bit_depth, channels, stereo_mode, packed=False):
         payload = np.ascontiguousarray(payload, dtype=np.uint8)
         bs = np.ascontiguousarray(block_sizes, dtype=np.uint32)
-        bb = np.ascontiguousarray(block_bytes, dtype=np.uint32)
+        bb = np.ascontiguousarray(block_bytes, dtype=np.uint32) if block_bytes is not None else None
+        bbp = bb.ctypes.data_as(u32p) if bb is not None else None  # None: serial v2 stream
         frames = int(bs.astype(np.uint64).sum())
         prm = DecParams(bit_depth, channels, stereo_mode)
         err = Err()
         if packed:
             out = np.zeros(frames * channels * (bit_depth // 8), dtype=np.uint8)
             rc = self.lib.lacb_decode(self.h, C.byref(prm), payload.ctypes.data, payload.size, bs.ctypes.data_as(u32p),
-                                      bb.ctypes.data_as(u32p), bs.size, LACB_PACKED_LE, out.ctypes.data, None,
-                                      C.byref(err))
+                                      bbp, bs.size, LACB_PACKED_LE, out.ctypes.data, None, C.byref(err))
             res = (out,)
         else:
             left = np.zeros(frames, dtype=np.int32)
             right = np.zeros(frames if channels == 2 else 0, dtype=np.int32)
             rc = self.lib.lacb_decode(self.h, C.byref(prm), payload.ctypes.data, payload.size, bs.ctypes.data_as(u32p),
-                                      bb.ctypes.data_as(u32p), bs.size, LACB_PLANAR_I32, left.ctypes.data,
+                                      bbp, bs.size, LACB_PLANAR_I32, left.ctypes.data,
                                       right.ctypes.data if channels == 2 else None, C.byref(err))
             res = (left, right)
         if rc == LACB_EDECODE:
@@ -345,22 +345,23 @@ class Codec:
         hdr = FrameHeader.parse(data)
         if hdr is None:
             fail("invalid frame header")
-        if hdr.version != 3:
-            fail("serial v2 streams are not supported by the GPU path")
+        v3 = hdr.version >= 3
         body = memoryview(data)[10:]
         if len(body) < 4:
             fail("invalid block count")
         nb = struct.unpack(">I", body[:4])[0]
         if nb == 0 or nb > MAX_BLOCK_COUNT:
             fail("invalid block count")
-        if nb > ((len(body) - 4) * 8) // 64:
+        words = 2 if v3 else 1
+        if nb > ((len(body) - 4) * 8) // (32 * words):
             fail("truncated block size table")
-        table = np.frombuffer(body[4:4 + 8 * nb], dtype=">u4").reshape(nb, 2).astype(np.uint64)
-        sizes, cbytes = table[:, 0], table[:, 1]
+        table = np.frombuffer(body[4:4 + 4 * words * nb], dtype=">u4").reshape(nb, words).astype(np.uint64)
+        sizes = table[:, 0]
+        cbytes = table[:, 1] if v3 else np.ones(nb, dtype=np.uint64)
         bad = (sizes == 0) | (sizes > MAX_BLOCK)
         bad[:-1] |= sizes[:-1] < 256
-        csum_s, csum_b = np.cumsum(sizes), np.cumsum(cbytes)
-        avail = len(body) - 4 - 8 * nb
+        csum_s, csum_b = np.cumsum(sizes), np.cumsum(cbytes if v3 else np.zeros(nb, dtype=np.uint64))
+        avail = len(body) - 4 - 4 * words * nb
         # errors are reported in table order, interleaved as the reference's loop does
         for i in range(nb) if (bad.any() or (cbytes == 0).any() or csum_s[-1] > MAX_TOTAL_SAMPLES
                                or csum_b[-1] > len(body)) else ():
@@ -378,8 +379,14 @@ class Codec:
         wav = total * hdr.channels * (hdr.bit_depth // 8)
         if 36 + wav + (wav & 1) > 0xFFFFFFFF:
             fail("decoded WAV data exceeds RIFF limit")
-        if int(csum_b[-1]) != avail:
+        if v3 and int(csum_b[-1]) != avail:
             fail("compressed block sizes do not match frame payload")
+        payload = np.frombuffer(body[4 + 4 * words * nb:], dtype=np.uint8)
+        if not v3:
+            left, right = self.decode_blocks(payload, sizes.astype(np.uint32), None, hdr.bit_depth, hdr.channels,
+                                             hdr.stereo_mode)
+            return left, right, dict(channels=hdr.channels, sample_rate=hdr.sample_rate, bit_depth=hdr.bit_depth,
+                                     stereo_mode=hdr.stereo_mode)
         payload = np.frombuffer(body[4 + 8 * nb:], dtype=np.uint8)
         left, right = self.decode_blocks(payload, sizes.astype(np.uint32), cbytes.astype(np.uint32), hdr.bit_depth,
                                          hdr.channels, hdr.stereo_mode)

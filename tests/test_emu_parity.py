@@ -87,3 +87,13 @@ def test_decoder_error_messages(cd):
         if a is not None:
             assert np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1])
     assert n >= 1
+
+
+def test_serial_v2_stream(cd):
+    from test_gpu_parity import _to_v2
+    l, r, depth = H.stereo_corpus()["synth16"]
+    v2 = _to_v2(H.oracle().encode(l, r, 48000, depth, 2))
+    dl, dr, hdr = cd.decode(v2)
+    assert np.array_equal(dl, l) and np.array_equal(dr, r)
+    with pytest.raises(RuntimeError, match="trailing frame payload"):
+        cd.decode(v2 + b"\0")

@@ -163,8 +163,39 @@ def test_frame_decoder_errors_match(cd):
             out_b, err_b = cd.decode(bad), None
         except RuntimeError as e:
             out_b, err_b = None, str(e)
-        if bad[2:3] == b"\x02" and err_a is None:
-            continue  # serial v2 streams are out of scope for the GPU path
         assert err_a == err_b
         if out_a is not None:
             assert np.array_equal(out_a[0], out_b[0]) and np.array_equal(out_a[1], out_b[1])
+
+
+def _to_v2(blob: bytes) -> bytes:
+    """Same blocks as a legacy v2 frame: version byte 2, table of sample counts only."""
+    import struct
+    hdr = bytearray(blob[:10])
+    hdr[2] = 2
+    nb = struct.unpack(">I", blob[10:14])[0]
+    tab = np.frombuffer(blob[14:14 + 8 * nb], dtype=">u4").reshape(nb, 2)
+    return bytes(hdr) + struct.pack(">I", nb) + tab[:, 0].astype(">u4").tobytes() + blob[14 + 8 * nb:]
+
+
+@pytest.mark.parametrize("name", ["synth16", "walk_plus_noise", "short_17_24bit"])
+def test_serial_v2_streams(cd, name):
+    """lac/decoder.cpp:209-218: v2 frames are one serial chain; same samples, same verdicts."""
+    l, r, depth = H.stereo_corpus()[name]
+    rng = np.random.default_rng(8)
+    for mode in (0, 1, 2):
+        v2 = _to_v2(H.oracle().encode(l, r, 48000, depth, mode))
+        dl, dr, hdr = cd.decode(v2)
+        assert np.array_equal(dl, l) and np.array_equal(dr, r)
+        for bad in _mutations(v2, rng, 20):
+            try:
+                a, ea = H.oracle().decode(bad), None
+            except RuntimeError as e:
+                a, ea = None, str(e)
+            try:
+                g, eg = cd.decode(bad), None
+            except RuntimeError as e:
+                g, eg = None, str(e)
+            assert ea == eg
+            if a is not None:
+                assert np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1])
