@@ -1,0 +1,3 @@
+// Compatibility shim: the reference header of this name, served by the GPU facade.
+#pragma once
+#include "lac_host.hpp"

@@ -224,23 +224,102 @@ bool FrameHeader::parse(const uint8_t* d, size_t size, FrameHeader& out, size_t&
   return true;
 }
 
+void FrameHeader::write(BitWriter& w) const {
+  std::vector<uint8_t> b;
+  append_to(b);
+  for (uint8_t x : b) w.write_bits(x, 8);
+}
+void FrameHeader::read(BitReader& r) {
+  sync = (uint16_t)r.read_bits(16);
+  version = (uint8_t)r.read_bits(8);
+  channels = (uint8_t)r.read_bits(8);
+  stereo_mode = (uint8_t)r.read_bits(8);
+  const uint32_t lo = r.read_bits(16), hi = r.read_bits(8);
+  bit_depth = (uint8_t)r.read_bits(8);
+  reserved = (uint8_t)r.read_bits(8);
+  sample_rate = lo | (hi << 16);
+}
+
 uint32_t BitReader::read_bits(int nbits) {
   if (nbits <= 0) return 0;
-  if (error_ || (size_t)nbits > size_ * 8 - pos_) {
+  if (error_ || pos_ >= size_ * 8 || (size_t)nbits > size_ * 8 - pos_) {
     mark_error();
     return 0;
   }
   uint32_t v = 0;
-  for (int i = 0; i < nbits; ++i, ++pos_) v = (v << 1) | ((data_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1u);
+  for (int i = 0; i < nbits; ++i, ++pos_) {
+    const uint32_t bit = (data_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1u;
+    if (i < 32) v = (v << 1) | bit;
+  }
   return v;
+}
+bool BitReader::read_unary_ones(uint32_t max_ones, uint32_t& ones) {
+  // ones up to a 0 terminator; more than max_ones, or running out of data, fails
+  uint32_t n = 0;
+  ones = 0;
+  while (!error_ && pos_ < size_ * 8) {
+    const uint32_t bit = (data_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1u;
+    if (!bit) {
+      ++pos_;
+      ones = n;
+      return true;
+    }
+    if (n == max_ones) {
+      ones = n;
+      return false;
+    }
+    ++n;
+    ++pos_;
+  }
+  ones = n;
+  mark_error();
+  return false;
+}
+void BitReader::align_to_byte() {
+  if (!error_) pos_ = (pos_ + 7) & ~(size_t)7;
+  if (pos_ > size_ * 8) mark_error();
+}
+bool BitReader::consume_zero_padding_to_byte() {
+  while (pos_ & 7) {
+    if (read_bits(1) != 0u || error_) return false;
+  }
+  return true;
 }
 void BitReader::advance_bits(size_t n) {
   if (error_ || n > size_ * 8 - pos_) mark_error();
   else pos_ += n;
 }
 
+void BitWriter::write_bit(uint32_t bit) {
+  cur_ = (uint8_t)((cur_ << 1) | (bit & 1u));
+  if (++nbits_ == 8) {
+    buffer_.push_back(cur_);
+    cur_ = 0;
+    nbits_ = 0;
+  }
+}
+void BitWriter::write_bits(uint32_t value, int nbits) {
+  for (int i = nbits - 1; i >= 0; --i) write_bit(i >= 32 ? 0u : (value >> i) & 1u);
+}
+void BitWriter::write_unary_ones(uint32_t ones) {
+  for (uint32_t i = 0; i < ones; ++i) write_bit(1u);
+}
+void BitWriter::write_bytes(const uint8_t* data, size_t size) {
+  for (size_t i = 0; i < size; ++i) write_bits(data[i], 8);
+}
+void BitWriter::flush_to_byte() {
+  while (nbits_ != 0) write_bit(0u);
+}
+std::vector<uint8_t> BitWriter::take_buffer() {
+  std::vector<uint8_t> out;  // complete bytes only, like get_buffer(); callers flush first
+  out.swap(buffer_);
+  return out;
+}
+
 // ---------------------------------------------------------------------------
 namespace lacb_host {
+lacb_ctx* shared_context(int device) { return ctx_for(device); }
+std::mutex& shared_context_mutex(int device) { return g_slots[device].mu; }
 int device_count() { return lacb_device_count(); }
 size_t resolve_devices(size_t requested) {
   if (requested == 0) {
@@ -441,8 +520,10 @@ std::vector<uint8_t> Encoder::encode(const std::vector<int32_t>& pcm) {
 
 bool Decoder::decode(BitReader& br, uint32_t block_size, std::vector<int32_t>& out) {
   if (block_size == 0 || block_size > kMaxBlock) return false;
-  out.assign(block_size, 0);
-  return decode_into(br, block_size, out.data());
+  std::vector<int32_t> pcm(block_size);
+  if (!decode_into(br, block_size, pcm.data())) return false;  // `out` untouched on failure
+  out.swap(pcm);
+  return true;
 }
 
 bool Decoder::decode_into(BitReader& br, uint32_t block_size, int32_t* out) {

@@ -22,17 +22,23 @@
 #include <thread>
 #include <vector>
 
+class BitReader;
+class BitWriter;
+
 struct FrameHeader {
   uint16_t sync = 0x4C41;
   uint8_t version = 3;
-  uint8_t channels = 1;
-  uint8_t stereo_mode = 0;
+  uint8_t channels = 2;      // defaults as in frame/frame_header.hpp:19-27
+  uint8_t stereo_mode = 2;
   uint32_t sample_rate = 44100;
   uint8_t bit_depth = 16;
   uint8_t reserved = 0;
 
   static constexpr size_t kBytes = 10;
   void append_to(std::vector<uint8_t>& out) const;
+  void write(BitWriter& w) const;
+  void read(BitReader& r);
+  bool validate() const { return valid(); }
   bool valid() const;
   // parses and validates; header_bytes receives 10 on success
   static bool parse(const uint8_t* data, size_t size, FrameHeader& out, size_t& header_bytes);
@@ -42,13 +48,19 @@ struct FrameHeader {
   }
 };
 
-// Minimal MSB-first reader: the GPU decoder consumes whole byte ranges, so the facade only
-// needs position bookkeeping compatible with Block::Decoder's (BitReader&, ...) signature.
+// MSB-first bit reader / writer with the reference's interface
+// (bitstream/bit_reader.hpp:6-30, bit_writer.hpp:6-23).  Host-side utilities: the GPU
+// decoder consumes whole byte ranges, these exist so code that hand-builds or inspects
+// streams (the reference's unit tests) keeps compiling.
 class BitReader {
  public:
   BitReader(const uint8_t* data, size_t size) : data_(data), size_(size) {}
-  explicit BitReader(const std::vector<uint8_t>& buf) : data_(buf.data()), size_(buf.size()) {}
+  BitReader(const std::vector<uint8_t>& buf) : data_(buf.data()), size_(buf.size()) {}
+  uint32_t read_bit() { return read_bits(1); }
   uint32_t read_bits(int nbits);
+  bool read_unary_ones(uint32_t max_ones, uint32_t& ones);
+  void align_to_byte();
+  bool consume_zero_padding_to_byte();
   size_t bits_remaining() const { return error_ ? 0 : size_ * 8 - pos_; }
   bool has_error() const { return error_; }
   bool eof() const { return bits_remaining() == 0; }
@@ -63,6 +75,24 @@ class BitReader {
   size_t size_;
   size_t pos_ = 0;
   bool error_ = false;
+};
+
+class BitWriter {
+ public:
+  BitWriter() = default;
+  void write_bit(uint32_t bit);
+  void write_bits(uint32_t value, int nbits);
+  void write_unary_ones(uint32_t ones);
+  void write_bytes(const uint8_t* data, size_t size);
+  void reserve_bytes(size_t size) { buffer_.reserve(size); }
+  void flush_to_byte();
+  const std::vector<uint8_t>& get_buffer() const { return buffer_; }
+  std::vector<uint8_t> take_buffer();
+
+ private:
+  std::vector<uint8_t> buffer_;  // complete bytes
+  uint8_t cur_ = 0;              // partial byte, MSB first
+  int nbits_ = 0;                // bits held in cur_
 };
 
 namespace LAC {
@@ -137,6 +167,18 @@ class Decoder {
 }  // namespace LAC
 
 namespace Block {
+
+// block/constants.hpp:6-15
+constexpr uint32_t MAX_BLOCK_SIZE = 16384;
+constexpr uint32_t MIN_CANONICAL_NON_FINAL_BLOCK_SIZE = 256;
+constexpr uint32_t ZERO_RUN_MIN_LENGTH = 4;
+constexpr uint32_t ZERO_RUN_LENGTH_K = 2;
+constexpr uint32_t MIN_PARTITION_SIZE = 32;
+constexpr uint8_t MAX_PARTITION_ORDER = 8;
+constexpr uint8_t PARTITION_FLAG = 0x80;
+constexpr uint8_t RESIDUAL_RESERVED_MASK = 0x10;
+constexpr uint8_t PARTITION_ORDER_SHIFT = 0;
+constexpr uint8_t PARTITION_ORDER_MASK = 0x0F;
 
 class Encoder {
  public:

@@ -135,3 +135,51 @@ bool write_wav_planes(const std::string& path, const WavInfo& info, const std::v
   }
   return write_wav_packed(path, info, pcm.data(), pcm.size());
 }
+
+bool read_wav(const std::string& path, std::vector<int32_t>& left, std::vector<int32_t>& right, uint16_t& channels,
+              uint32_t& sample_rate, uint8_t& bit_depth) {
+  left.clear();
+  right.clear();
+  channels = 0;
+  sample_rate = 0;
+  bit_depth = 0;
+  WavInfo info;
+  std::vector<uint8_t> pcm;
+  if (!read_wav_packed(path, info, pcm)) return false;
+  unpack_planes(info, pcm.data(), left, right);
+  channels = info.channels;
+  sample_rate = info.sample_rate;
+  bit_depth = info.bit_depth;
+  return true;
+}
+
+static bool write_wav_common(const std::string& path, const std::vector<int32_t>& left,
+                             const std::vector<int32_t>& right, uint16_t channels, uint32_t sample_rate,
+                             uint8_t bit_depth, bool check) {
+  if ((channels != 1 && channels != 2) || (bit_depth != 16 && bit_depth != 24) || !rate_ok(sample_rate)) return false;
+  if (left.empty()) return false;
+  if (channels == 2 && right.size() != left.size()) return false;
+  if (channels == 1 && !right.empty()) return false;
+  if (check) {
+    const int32_t lo = bit_depth == 16 ? -32768 : -8388608, hi = bit_depth == 16 ? 32767 : 8388607;
+    for (int32_t v : left)
+      if (v < lo || v > hi) return false;
+    for (int32_t v : right)
+      if (v < lo || v > hi) return false;
+  }
+  WavInfo info;
+  info.channels = channels;
+  info.sample_rate = sample_rate;
+  info.bit_depth = bit_depth;
+  info.frames = left.size();
+  return write_wav_planes(path, info, left, right);
+}
+bool write_wav(const std::string& path, const std::vector<int32_t>& left, const std::vector<int32_t>& right,
+               uint16_t channels, uint32_t sample_rate, uint8_t bit_depth) {
+  return write_wav_common(path, left, right, channels, sample_rate, bit_depth, true);
+}
+bool write_wav_unchecked_samples(const std::string& path, const std::vector<int32_t>& left,
+                                 const std::vector<int32_t>& right, uint16_t channels, uint32_t sample_rate,
+                                 uint8_t bit_depth) {
+  return write_wav_common(path, left, right, channels, sample_rate, bit_depth, false);
+}

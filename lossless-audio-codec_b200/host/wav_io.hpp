@@ -28,3 +28,12 @@ bool write_wav_packed(const std::string& path, const WavInfo& info, const uint8_
 bool write_wav_planes(const std::string& path, const WavInfo& info, const std::vector<int32_t>& left,
                       const std::vector<int32_t>& right);
 void unpack_planes(const WavInfo& info, const uint8_t* pcm, std::vector<int32_t>& left, std::vector<int32_t>& right);
+
+// The reference's int32-plane interface (src/io/wav_io.hpp:6-26).
+bool read_wav(const std::string& path, std::vector<int32_t>& left, std::vector<int32_t>& right, uint16_t& channels,
+              uint32_t& sample_rate, uint8_t& bit_depth);
+bool write_wav(const std::string& path, const std::vector<int32_t>& left, const std::vector<int32_t>& right,
+               uint16_t channels, uint32_t sample_rate, uint8_t bit_depth);
+bool write_wav_unchecked_samples(const std::string& path, const std::vector<int32_t>& left,
+                                 const std::vector<int32_t>& right, uint16_t channels, uint32_t sample_rate,
+                                 uint8_t bit_depth);
