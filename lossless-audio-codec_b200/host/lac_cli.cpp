@@ -4,12 +4,14 @@
 // (default: auto per block), --threads=N / LAC_THREADS, --debug-threads, --no-partitioning;
 // plus --devices=N / LAC_DEVICES to shard the block range across GPUs.  Files are written
 // to a private temporary name and published with rename(), and input == output is refused.
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -53,13 +55,45 @@ bool load_file(const std::string& path, std::vector<uint8_t>& out, uint64_t cap)
   return ok;
 }
 
-// write to "<path>.tmp.<pid>" and rename over the destination only when complete
+// Output is written inside a private (0700) temporary directory next to the destination and
+// published with rename(): a failed run never touches an existing file, hard links and
+// symlinks at the destination are replaced rather than written through, long file names and
+// a restrictive umask work (the staging name is short and its mode is set explicitly).
 struct Staged {
-  std::string final_path, tmp_path;
-  explicit Staged(const std::string& p) : final_path(p), tmp_path(p + ".tmp." + std::to_string((long)getpid())) {}
-  bool publish() { return std::rename(tmp_path.c_str(), final_path.c_str()) == 0; }
-  ~Staged() { std::remove(tmp_path.c_str()); }
+  std::filesystem::path final_path, tmp_dir, tmp_path;
+  bool ok = false;
+  explicit Staged(const std::string& p) : final_path(p) {
+    std::filesystem::path parent = final_path.parent_path();
+    if (parent.empty()) parent = ".";
+    static int counter = 0;
+    tmp_dir = parent / (".lacb-stage-" + std::to_string((long)getpid()) + "-" + std::to_string(counter++));
+    if (::mkdir(tmp_dir.c_str(), 0700) == 0) {
+      ::chmod(tmp_dir.c_str(), 0700);
+      tmp_path = tmp_dir / "out";
+      ok = true;
+    }
+  }
+  bool publish() {
+    if (!ok) return false;
+    std::error_code ec;
+    std::filesystem::rename(tmp_path, final_path, ec);
+    return !ec;
+  }
+  ~Staged() {
+    std::error_code ec;
+    if (ok) {
+      std::filesystem::remove(tmp_path, ec);
+      std::filesystem::remove(tmp_dir, ec);
+    }
+  }
 };
+
+bool same_file(const std::string& a, const std::string& b) {
+  if (a == b) return true;
+  std::error_code ec;
+  if (!std::filesystem::exists(b, ec)) return false;
+  return std::filesystem::equivalent(a, b, ec) && !ec;
+}
 
 bool save_file(const std::string& path, const std::vector<uint8_t>& bytes) {
   FILE* f = std::fopen(path.c_str(), "wb");
@@ -125,7 +159,7 @@ int main(int argc, char** argv) {
       return 1;
     }
     const std::string in_path = argv[2], out_path = argv[3];
-    if (in_path == out_path) {
+    if (same_file(in_path, out_path)) {
       std::cerr << "Input and output paths must be different\n";
       return 1;
     }
@@ -165,7 +199,7 @@ int main(int argc, char** argv) {
       enc.set_device_count(devices);
       const std::vector<uint8_t> bitstream = enc.encode_packed(pcm.data(), info.frames, (uint8_t)info.channels, &tc);
       Staged st(out_path);
-      if (!save_file(st.tmp_path, bitstream) || !st.publish()) {
+      if (!st.ok || !save_file(st.tmp_path.string(), bitstream) || !st.publish()) {
         std::cerr << "Failed to write LAC file: " << out_path << "\n";
         return 1;
       }
@@ -197,7 +231,7 @@ int main(int argc, char** argv) {
     info.bit_depth = hdr.bit_depth;
     info.frames = frames;
     Staged st(out_path);
-    if (!write_wav_packed(st.tmp_path, info, pcm.data(), pcm.size()) || !st.publish()) {
+    if (!st.ok || !write_wav_packed(st.tmp_path.string(), info, pcm.data(), pcm.size()) || !st.publish()) {
       std::cerr << "Failed to write WAV: " << out_path << "\n";
       return 1;
     }
