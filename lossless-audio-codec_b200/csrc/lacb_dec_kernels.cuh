@@ -281,23 +281,44 @@ struct ChanHdr {
   int16_t coef[33];
 };
 
-// Header + residual part of Block::Decoder::decode_into (block/decoder.cpp:64-512):
-// leaves the residual in `out` and the predictor description in `hdr`.
 // Per-warp scratch of the speculative token batches.
 struct ParseScratch {
-  uint32_t uval[32];
-  uint32_t wval[32];
-  uint32_t twi[33];   // reader position before token t: word index ...
-  uint32_t tav[33];   // ... and valid bits in the window (pos = wi * 32 - avail)
+  uint32_t ring[128];  // big-endian words of the bitstream, slot = word index & 127
+  uint32_t tp[34];     // bit offset of every token of the batch from the word-aligned batch base; [cnt] = end
+};
+// staged word range [lo, hi) of the ring (warp-uniform registers)
+struct Stage {
+  uint32_t lo, hi;
 };
 
-// One token of a stateless adaptive segment (lane 0 only): value u, sample count w.
-//   MODE_RICE: Rice(k)                          block/decoder.cpp:126-136
-//   MODE_ZR  : tag 00 Rice(k) | 01 run | 10 raw block/decoder.cpp:138-257
+// Makes sure the 64 words from the one holding bit `pos` are in the ring: a batch of 32 tokens
+// spans at most 32 * 58 + 31 bits and every token is looked at through a 2-word window.
+__device__ __forceinline__ void stage_ensure(const BitRd& r, ParseScratch* sc, Stage& sg, u64 pos, uint32_t lane) {
+  const u64 wq = pos >> 5;
+  const uint32_t wi = wq > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)wq;
+  if (wi < sg.lo || wi > sg.hi) sg.lo = sg.hi = wi;  // outside the staged range: start over
+  bool any = false;
+  while (sg.hi < wi + 64u) {  // the slots overwritten hold words below wi - 32
+    sc->ring[(sg.hi + lane) & 127u] = rd_word(r, sg.hi + lane);
+    sg.hi += 32u;
+    any = true;
+  }
+  if (sg.hi - sg.lo > 128u) sg.lo = sg.hi - 128u;
+  if (any) __syncwarp();
+}
+// 32 bits from bit `rel` after word `wbase`
+__device__ __forceinline__ uint32_t ring_peek(const uint32_t* ring, uint32_t wbase, uint32_t rel) {
+  const uint32_t wi = wbase + (rel >> 5);
+  return __funnelshift_l(ring[(wi + 1u) & 127u], ring[wi & 127u], rel);
+}
+
+// One token by the exact serial reader (lane 0 only): value u, sample count w.
+//   MODE_RICE / MODE_STATIC: Rice(k)             block/decoder.cpp:126-136, 296-303
+//   MODE_ZR  : tag 00 Rice(k) | 01 run | 10 raw  block/decoder.cpp:138-257
 //   MODE_BIN : tag 00 | 01 s | 10 s | 11 Rice(k) block/decoder.cpp:259-294
 __device__ __forceinline__ bool parse_token(BitRd& r, uint32_t mode, uint32_t k, uint32_t* u, uint32_t* w) {
   *w = 1u;
-  if (mode == MODE_RICE) return rd_rice(r, k, u);
+  if (mode == MODE_RICE || mode == MODE_STATIC) return rd_rice(r, k, u);
   const uint32_t tag = rd_get(r, 2u);
   if (mode == MODE_BIN) {
     if (tag == 0u) { *u = 0u; return true; }
@@ -316,93 +337,190 @@ __device__ __forceinline__ bool parse_token(BitRd& r, uint32_t mode, uint32_t k,
   return true;
 }
 
-// Warp-cooperative decode of one STATELESS adaptive segment (modes 0, 1, 2).
+// Lane 0: boundaries of up to B tokens under parameter k, nothing else -- per token one
+// 2-word window from the ring, a count-leading-ones and an add sit on the serial chain.
+// Stops in front of a token the exact reader has to look at (unary run not terminated inside
+// the view, reserved tag).  tp[0..cnt] = token starts / end, returns cnt.
+__device__ __forceinline__ uint32_t walk_tokens(const uint32_t* ring, uint32_t* tp, uint32_t wbase, uint32_t rel,
+                                                uint32_t mode, uint32_t k, uint32_t B) {
+  uint32_t cnt = 0u;
+  if (mode == MODE_RICE || mode == MODE_STATIC) {
+    const uint32_t k1 = k + 1u;
+    while (cnt < B) {
+      tp[cnt] = rel;
+      const uint32_t hi = ring_peek(ring, wbase, rel);
+      if (hi == 0xFFFFFFFFu) break;
+      rel += (uint32_t)__clz((int)~hi) + k1;
+      ++cnt;
+    }
+  } else if (mode == MODE_ZR) {
+    while (cnt < B) {
+      tp[cnt] = rel;
+      const uint32_t hi = ring_peek(ring, wbase, rel);
+      const uint32_t tag = hi >> 30;
+      if (tag == 3u) break;
+      if (tag == 2u) {
+        rel += 34u;
+      } else {
+        const uint32_t q = (uint32_t)__clz((int)~((hi << 2) | 3u));
+        if (q >= 30u) break;
+        rel += 3u + q + (tag ? kZrRunK : k);
+      }
+      ++cnt;
+    }
+  } else {  // MODE_BIN
+    while (cnt < B) {
+      tp[cnt] = rel;
+      const uint32_t hi = ring_peek(ring, wbase, rel);
+      const uint32_t tag = hi >> 30;
+      if (tag == 0u) {
+        rel += 2u;
+      } else if (tag != 3u) {
+        rel += 3u;
+      } else {
+        const uint32_t q = (uint32_t)__clz((int)~((hi << 2) | 3u));
+        if (q >= 30u) break;
+        rel += 3u + q + k;
+      }
+      ++cnt;
+    }
+  }
+  tp[cnt] = rel;
+  return cnt;
+}
+
+// Warp-cooperative decode of one segment whose Rice parameter is either fixed (MODE_STATIC)
+// or follows the STATELESS model (block/encoder.cpp:72-77: a function of the sum of u and
+// the sample count only).
 //
-// The stateless k (block/encoder.cpp:72-77) depends only on (sum of u, sample count), so a
-// batch of tokens parsed by lane 0 under the assumption "k stays k" can be checked by the
-// whole warp with one prefix scan: lane i recomputes the k that follows token i; the first
-// lane whose k differs ends the valid prefix, the reader is rewound to the next token and
-// the batch restarts with the new k.  Valid tokens are committed with coalesced stores.
-// All lanes must call this; only lane 0's reader `r` is meaningful.
-__device__ __forceinline__ bool decode_segment_warp(BitRd& r, uint32_t n, uint32_t k0, uint32_t mode, int32_t* res,
-                                                    ParseScratch* sc, uint32_t lane) {
+// Lane 0 walks the token boundaries of a batch assuming "k stays k"; lane t then extracts
+// token t from its two boundaries, and one prefix scan over the batch gives every lane the k
+// that follows its token.  The first lane whose k differs ends the valid prefix: its tokens
+// are committed with coalesced stores and the batch restarts behind it with the new k.  A
+// token the walker cannot place (long unary run, reserved tag, data or run running past the
+// end) is handed to the exact serial reader once everything in front of it is verified, so
+// every accept / reject verdict is the serial decoder's.  `pos` (absolute bit position, same
+// in all lanes) is advanced past the segment.
+__device__ __forceinline__ bool decode_segment_fast(BitRd& r, u64& pos, uint32_t n, uint32_t k0, uint32_t mode,
+                                                    int32_t* res, ParseScratch* sc, Stage& stg, uint32_t lane) {
+  const bool adaptive = mode != MODE_STATIC;
   u64 sum = 0ull;
-  uint32_t count = 0u, idx = 0u, k = k0, B = 8u;
+  uint32_t count = 0u, idx = 0u, k = k0, B = adaptive ? 8u : 32u;
   if (k0 > 31u) return false;
   while (idx < n) {
-    uint32_t cnt = 0u, bad = 0u;
-    if (lane == 0u) {
-      const uint32_t left = n - idx;
-      uint32_t used = 0u;
-      while (cnt < B && used < left) {
-        sc->twi[cnt] = r.wi;
-        sc->tav[cnt] = r.avail;
-        uint32_t u, w;
-        if (!parse_token(r, mode, k, &u, &w) || w > left - used) {
-          bad = 1u;
-          break;
-        }
-        sc->uval[cnt] = u;
-        sc->wval[cnt] = w;
-        used += w;
-        ++cnt;
-      }
-      if (!bad) {
-        sc->twi[cnt] = r.wi;
-        sc->tav[cnt] = r.avail;
-        if (rd_over(r)) {  // ran past the block: the last token cannot stand (checked once per batch)
-          bad = 1u;
-          --cnt;
-        }
-      }
-    }
+    const uint32_t left = n - idx;
+    const uint32_t want = k > 26u ? 0u : (B < left ? B : left);  // k > 26: the unary limit can bind, serial reader
+    stage_ensure(r, sc, stg, pos, lane);
+    const uint32_t wbase = (uint32_t)(pos >> 5), rel0 = (uint32_t)pos & 31u;
+    uint32_t cnt = 0u;
+    if (lane == 0u && want) cnt = walk_tokens(sc->ring, sc->tp, wbase, rel0, mode, k, want);
     cnt = __shfl_sync(kFull, cnt, 0);
-    bad = __shfl_sync(kFull, bad, 0);
     __syncwarp();
-    if (cnt == 0u) return false;  // the very next token fails under the true k
-    const uint32_t u = lane < cnt ? sc->uval[lane] : 0u;
-    const uint32_t w = lane < cnt ? sc->wval[lane] : 0u;
-    u64 PU = u;
-    uint32_t PW = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u64 yu = __shfl_up_sync(kFull, PU, d);
-      const uint32_t yw = __shfl_up_sync(kFull, PW, d);
-      if (lane >= (uint32_t)d) {
-        PU += yu;
-        PW += yw;
-      }
-    }
-    const uint32_t c = count + PW;
-    const uint32_t knext = c ? kbase_clz(sum + PU + (c >> 1), c) : 0u;
-    const uint32_t mism = __ballot_sync(kFull, lane < cnt && knext != k);
-    const uint32_t valid = mism ? (uint32_t)__ffs((int)mism) : cnt;  // tokens [0, valid) used the right k
-    if (lane < valid) {
-      int32_t* dst = res + idx + (PW - w);
-      if (w == 1u) {
-        dst[0] = unzz32(u);
+    uint32_t u = 0u, w = 0u;
+    bool bad = false;
+    if (lane < cnt) {
+      const uint32_t s = sc->tp[lane], e = sc->tp[lane + 1u];
+      bad = (u64)wbase * 32ull + e > r.end;
+      w = 1u;
+      if (mode == MODE_RICE || mode == MODE_STATIC) {
+        const uint32_t rem = k ? ring_peek(sc->ring, wbase, e - k) >> (32u - k) : 0u;
+        u = ((e - s - 1u - k) << k) | rem;
       } else {
-        for (uint32_t j = 0; j < w; ++j) dst[j] = 0;
+        const uint32_t hs = ring_peek(sc->ring, wbase, s);
+        const uint32_t tag = hs >> 30;
+        if (mode == MODE_ZR && tag == 2u) {
+          u = ring_peek(sc->ring, wbase, s + 2u);
+        } else if (mode == MODE_ZR && tag == 1u) {
+          const uint32_t rem = ring_peek(sc->ring, wbase, e - kZrRunK) >> (32u - kZrRunK);
+          w = (((e - s - 3u - kZrRunK) << kZrRunK) | rem) + kZrMinRun;
+        } else if (mode == MODE_BIN && tag != 3u) {
+          const uint32_t sign = (hs >> 29) & 1u;
+          u = tag == 0u ? 0u : (tag == 1u ? (sign ? 1u : 2u) : (sign ? 3u : 4u));
+        } else {  // tag 00 (zero-run mode) / 11 (bin mode): Rice(k) behind the tag
+          const uint32_t rem = k ? ring_peek(sc->ring, wbase, e - k) >> (32u - k) : 0u;
+          u = ((e - s - 3u - k) << k) | rem;
+        }
       }
     }
-    const uint32_t knew = __shfl_sync(kFull, knext, (int)valid - 1);
-    sum += __shfl_sync(kFull, PU, (int)valid - 1);
-    const uint32_t adv = __shfl_sync(kFull, PW, (int)valid - 1);
-    count += adv;
-    idx += adv;
-    const bool all_ok = (valid == cnt) && (knew == k);
-    if (bad && all_ok) return false;  // the failing token was parsed with the correct k
-    if (!all_ok || bad) {
-      if (lane == 0u) rd_seek(r, (u64)sc->twi[valid] * 32ull - sc->tav[valid]);
-      B = valid < 4u ? 4u : valid;
+    uint32_t PW = w;
+    u64 PU = u;
+    uint32_t knext = k;
+    if (adaptive) {
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const u64 yu = __shfl_up_sync(kFull, PU, d);
+        const uint32_t yw = __shfl_up_sync(kFull, PW, d);
+        if (lane >= (uint32_t)d) {
+          PU += yu;
+          PW += yw;
+        }
+      }
+      const uint32_t c = count + PW;
+      knext = c ? kbase_clz(sum + PU + (c >> 1), c) : 0u;
     } else {
-      B = B * 2u > 32u ? 32u : B * 2u;
+      PW = lane + 1u;  // one sample per token, the scan is not needed
     }
-    k = knew;
+    bad = bad || (lane < cnt && PW > left);
+    const uint32_t mbad = __ballot_sync(kFull, bad);
+    const uint32_t mism = __ballot_sync(kFull, lane < cnt && knext != k);
+    uint32_t valid = mism ? (uint32_t)__ffs((int)mism) : cnt;  // tokens [0, valid) were read with the right k
+    const uint32_t first_bad = mbad ? (uint32_t)__ffs((int)mbad) - 1u : cnt;
+    if (valid > first_bad) valid = first_bad;
+    uint32_t knew = k;
+    if (valid) {
+      if (lane < valid && w == 1u) res[idx + PW - 1u] = unzz32(u);
+      uint32_t runs = __ballot_sync(kFull, lane < valid && w > 1u);
+      while (runs) {  // zero runs are filled by the whole warp
+        const int t = __ffs((int)runs) - 1;
+        runs &= runs - 1u;
+        const uint32_t o = __shfl_sync(kFull, PW - w, t), len = __shfl_sync(kFull, w, t);
+        for (uint32_t j = lane; j < len; j += 32u) res[idx + o + j] = 0;
+      }
+      knew = __shfl_sync(kFull, knext, (int)valid - 1);
+      sum += __shfl_sync(kFull, PU, (int)valid - 1);
+      const uint32_t adv = __shfl_sync(kFull, PW, (int)valid - 1);
+      count += adv;
+      idx += adv;
+      pos = (u64)wbase * 32ull + sc->tp[valid];
+    }
+    if (knew != k) {  // k moved behind token valid-1: what follows was read with the wrong k
+      k = knew;
+      B = valid < 4u ? 4u : valid;
+      __syncwarp();
+      continue;
+    }
+    if (valid == cnt && cnt == want && want) {  // a clean full batch
+      B = B * 2u > 32u ? 32u : B * 2u;
+      __syncwarp();
+      continue;
+    }
+    if (idx >= n) break;
+    // The next token is one the walker stopped at, or it runs past the data / the segment:
+    // everything before it is verified, so the serial reader decides with the true k.
+    uint32_t ok = 0u, su = 0u, sw = 0u;
+    u64 npos = 0ull;
+    if (lane == 0u) {
+      rd_seek(r, pos);
+      ok = parse_token(r, mode, k, &su, &sw) && !rd_over(r) && sw <= n - idx;
+      npos = rd_pos(r);
+    }
+    ok = __shfl_sync(kFull, ok, 0);
+    if (!ok) return false;
+    su = __shfl_sync(kFull, su, 0);
+    sw = __shfl_sync(kFull, sw, 0);
+    pos = __shfl_sync(kFull, npos, 0);
+    if (sw == 1u) {
+      if (lane == 0u) res[idx] = unzz32(su);
+    } else {
+      for (uint32_t j = lane; j < sw; j += 32u) res[idx + j] = 0;
+    }
+    sum += su;
+    count += sw;
+    idx += sw;
+    if (adaptive) k = kbase_clz(sum + (count >> 1), count);
     __syncwarp();
   }
-  const uint32_t over = __shfl_sync(kFull, (uint32_t)rd_over(r), 0);
-  return over == 0u;
+  return true;
 }
 
 // Header + residual part of Block::Decoder::decode_into (block/decoder.cpp:64-512): leaves
@@ -449,14 +567,16 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
       const u64 tokens_pos = table_pos + 7ull * (1u << p);
       if (tokens_pos > r.end) break;
       if ((rd_get(r, 7u) >> 5) != cmode) break;
-      rd_seek(r, tokens_pos);
       ok = 1u;
     } while (false);
   }
   ok = __shfl_sync(kFull, ok, 0);
   p = __shfl_sync(kFull, p, 0);
   if (!ok) return false;
+  table_pos = __shfl_sync(kFull, table_pos, 0);
   const uint32_t cnt = 1u << p;
+  u64 pos = table_pos + 7ull * cnt;  // first token; kept identical in all lanes
+  Stage stg = {0xFFFFFFFFu, 0xFFFFFFFFu};
   uint32_t off = 0u;
   for (uint32_t i = 0; i < cnt; ++i) {
     uint32_t mk = 0u;
@@ -468,18 +588,22 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
     mk = __shfl_sync(kFull, mk, 0);
     const uint32_t len = part_len(n, p, i);
     const uint32_t mode = mk >> 5, k0 = mk & 31u;
-    if (p && mode != MODE_STATIC) {
-      ok = decode_segment_warp(r, len, k0, mode, out + off, sc, lane) ? 1u : 0u;
-    } else {
-      if (lane == 0u)
-        ok = (p ? decode_segment<true>(r, len, k0, mode, out + off, ring)
-                : decode_segment<false>(r, len, k0, mode, out + off, ring)) ? 1u : 0u;
+    if (p || mode == MODE_STATIC) {
+      ok = decode_segment_fast(r, pos, len, k0, mode, out + off, sc, stg, lane) ? 1u : 0u;
+    } else {  // stateful adaptation (p == 0): the serial reader with the full model
+      if (lane == 0u) {
+        rd_seek(r, pos);
+        ok = decode_segment<false>(r, len, k0, mode, out + off, ring) ? 1u : 0u;
+        pos = rd_pos(r);
+      }
       ok = __shfl_sync(kFull, ok, 0);
+      pos = __shfl_sync(kFull, pos, 0);
     }
     if (!ok) return false;
     off += len;
   }
   if (lane == 0u) {
+    rd_seek(r, pos);
     // consume_zero_padding_to_byte (bit_reader.hpp:180-185)
     const uint32_t padn = (uint32_t)((8ull - ((rd_pos(r) - r.start) & 7ull)) & 7ull);
     if (padn) {
@@ -491,39 +615,47 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
   return ok != 0u;
 }
 
-// Runs step(i, value&) over x[0..n) in order, 8 samples at a time: the next chunk's loads
-// are issued before the current chunk's dependent arithmetic (the in-place pattern
-// load x[i] -> store x[i] otherwise pays a full memory round trip per sample), and the
-// chunks move as 128-bit vectors when the plane is 16-byte aligned.
+// Runs step(i, value&) over x[0..n) in order, 8 samples at a time.  One thread owns the
+// whole serial recurrence, so the only thing that can hide the memory latency of the
+// in-place pattern (load x[i] -> compute -> store x[i]) is distance: the loads of chunk
+// c + D are issued when chunk c is taken out of its register slot, D = 4 chunks (32 samples,
+// ~1000 cycles of dependent arithmetic) ahead of their use.  Chunks move as 128-bit vectors
+// when the plane is 16-byte aligned (every block start of a regular stream is).
 template <typename Step>
 __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, Step&& step) {
+  constexpr int D = 4;
   const bool aligned = (reinterpret_cast<uint64_t>(x) & 15ull) == 0ull;
-  int32_t v[8], nv[8];
-  auto load8 = [&](uint32_t i, int32_t (&d)[8]) {
-    if (aligned) {
-      const int4 a = *reinterpret_cast<const int4*>(x + i), b = *reinterpret_cast<const int4*>(x + i + 4);
-      d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = x[i + j];
-    }
-  };
   uint32_t i = 0;
-  if (n >= 8u) load8(0u, v);
-  for (; i + 8u <= n; i += 8u) {
-    if (i + 16u <= n) load8(i + 8u, nv);
+  if (aligned) {
+    int4 buf[D][2];
+    const uint32_t nch = n >> 3;
+    int4* x4 = reinterpret_cast<int4*>(x);
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (!step(i + (uint32_t)j, v[j])) return false;
-    if (aligned) {
-      *reinterpret_cast<int4*>(x + i) = make_int4(v[0], v[1], v[2], v[3]);
-      *reinterpret_cast<int4*>(x + i + 4) = make_int4(v[4], v[5], v[6], v[7]);
-    } else {
+    for (int d = 0; d < D; ++d)
+      if ((uint32_t)d < nch) {
+        buf[d][0] = x4[2 * d];
+        buf[d][1] = x4[2 * d + 1];
+      }
+    for (uint32_t c0 = 0; c0 < nch; c0 += D) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[i + j] = v[j];
+      for (int d = 0; d < D; ++d) {
+        const uint32_t c = c0 + (uint32_t)d;
+        if (c < nch) {
+          int32_t v[8] = {buf[d][0].x, buf[d][0].y, buf[d][0].z, buf[d][0].w,
+                          buf[d][1].x, buf[d][1].y, buf[d][1].z, buf[d][1].w};
+          if (c + D < nch) {
+            buf[d][0] = x4[2 * (c + D)];
+            buf[d][1] = x4[2 * (c + D) + 1];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (!step(c * 8u + (uint32_t)j, v[j])) return false;
+          x4[2 * c] = make_int4(v[0], v[1], v[2], v[3]);
+          x4[2 * c + 1] = make_int4(v[4], v[5], v[6], v[7]);
+        }
+      }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = nv[j];
+    i = nch << 3;
   }
   for (; i < n; ++i) {
     int32_t t = x[i];

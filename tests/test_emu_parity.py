@@ -89,6 +89,13 @@ def test_decoder_error_messages(cd):
     assert n >= 1
 
 
+def test_block_decoder_fuzz_all_modes(cd):
+    from test_gpu_parity import fuzz_block_decoder
+    names = ["zr_sweep_n576", "bin_fallback_64", "sparse_4096", "mixed_runs_spikes_2048", "noise_n257", "pm2_4096",
+             "int32_noise_512", "alternating_4096"]
+    assert fuzz_block_decoder(cd, 7, names, 8) > 20
+
+
 def test_serial_v2_stream(cd):
     from test_gpu_parity import _to_v2
     l, r, depth = H.stereo_corpus()["synth16"]

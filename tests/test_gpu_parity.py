@@ -150,6 +150,40 @@ def test_block_decoder_verdicts_match(cd):
                 assert bits_a == bits_b and np.array_equal(dec_a, dec_b)
 
 
+def fuzz_block_decoder(cd, seed, names, flips):
+    """Every residual mode (partitioned or not, zero-run on/off): intact, truncated, extended and
+    bit-flipped streams must get the oracle's verdict, bit count and samples."""
+    rng = np.random.default_rng(seed)
+    corpus = H.block_corpus()
+    rejected = 0
+    for name in names:
+        pcm = corpus[name]
+        for zr, part in ((1, 1), (0, 1), (1, 0)):
+            good = H.oracle().block_encode(pcm, zr, part)
+            trials = [good, good[:-1], good[: len(good) // 2], good + b"\0"]
+            for _ in range(flips):
+                b = bytearray(good)
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+                trials.append(bytes(b))
+            for t in trials:
+                ok_a, dec_a, bits_a = H.oracle().block_decode(t, len(pcm))
+                ok_b, dec_b, bits_b = cd.block_decode(t, len(pcm))
+                assert ok_a == ok_b, (name, zr, part, len(t))
+                rejected += not ok_a
+                if ok_a:
+                    assert bits_a == bits_b and np.array_equal(dec_a, dec_b), (name, zr, part)
+    return rejected
+
+
+FUZZ_BLOCKS = ["zr_sweep_n576", "bin_fallback_64", "sparse_4096", "mixed_runs_spikes_2048", "noise_n257",
+               "noise_n1000", "level_steps_16384", "pm2_4096", "lownoise_16384", "sparse_bursts_16384",
+               "int32_noise_512", "zr_sweep_n320", "alternating_4096", "silence_then_noise_16384"]
+
+
+def test_block_decoder_fuzz_all_modes(cd):
+    assert fuzz_block_decoder(cd, 5, FUZZ_BLOCKS, 24) > 100
+
+
 def test_frame_decoder_errors_match(cd):
     rng = np.random.default_rng(6)
     l, r, depth = H.stereo_corpus()["walk_plus_noise"]
