@@ -41,6 +41,19 @@ typedef long long i64;
 __device__ __forceinline__ uint32_t zz32(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
 __device__ __forceinline__ int32_t unzz32(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
 
+// c + a * b with a signed 32 x 32 -> 64 bit multiply-add: spelled as the PTX instruction so the
+// operands stay 32-bit registers (the C form makes the compiler keep sign-extended 64-bit
+// copies of every sample, which doubles the register footprint of the FIR loops)
+__device__ __forceinline__ i64 mad_wide(int32_t a, int32_t b, i64 c) {
+#ifdef LACB_EMU
+  return (i64)((u64)((i64)a * (i64)b) + (u64)c);
+#else
+  i64 d;
+  asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+  return d;
+#endif
+}
+
 __device__ __forceinline__ uint32_t bitwidth64(u64 v) { return 64u - (uint32_t)__clzll((i64)v); }
 
 // Conflict-free shared-memory layout for "thread t owns E consecutive words":
@@ -180,12 +193,73 @@ __device__ __forceinline__ int32_t block_excl_max_i32(int32_t v, int32_t* scratc
   return ex;
 }
 
-__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+// Exclusive sum scan and exclusive running maximum (identity -1) of one value pair per thread
+// in a single pass: one barrier between the warp level and the block level.  `scratch` holds
+// 48 entries.  TRAIL adds the closing barrier that protects the scratch; callers that reach
+// another barrier before the scratch is written again pass false.
+template <int NT, bool TRAIL>
+__device__ __forceinline__ void block_scan_sum_max(u64 v, int32_t m, u64* scratch, u64* ex_sum, u64* total,
+                                                   int32_t* ex_max) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  constexpr int NW = (NT + 31) / 32;
+  u64 inc = v;
+  int32_t im = m;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
-  return v;
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 y = __shfl_up_sync(kFull, inc, d);
+    const int32_t ym = __shfl_up_sync(kFull, im, d);
+    if (lane >= (uint32_t)d) {
+      inc += y;
+      if (ym > im) im = ym;
+    }
+  }
+  int32_t exm = __shfl_up_sync(kFull, im, 1);
+  if (lane == 0u) exm = -1;
+  if (NW == 1) {
+    *total = __shfl_sync(kFull, inc, 31);
+    *ex_sum = inc - v;
+    *ex_max = exm;
+    __syncthreads();  // callers rely on one barrier inside the scan
+    return;
+  }
+  int32_t* smax = reinterpret_cast<int32_t*>(scratch + 32);
+  if (lane == 31u) {
+    scratch[w] = inc;
+    smax[w] = im;
+  }
+  __syncthreads();
+  u64 ws = (lane < (uint32_t)NW) ? scratch[lane] : 0ull;
+  int32_t wm = (lane < (uint32_t)NW) ? smax[lane] : -1;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 y = __shfl_up_sync(kFull, ws, d);
+    const int32_t ym = __shfl_up_sync(kFull, wm, d);
+    if (lane >= (uint32_t)d) {
+      ws += y;
+      if (ym > wm) wm = ym;
+    }
+  }
+  const u64 wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
+  const int32_t wmprev = __shfl_sync(kFull, wm, (int)((w + 31u) & 31u));
+  *total = __shfl_sync(kFull, ws, NW - 1);
+  if (TRAIL) __syncthreads();
+  *ex_sum = (w ? wprev : 0ull) + inc - v;
+  if (w && wmprev > exm) exm = wmprev;
+  *ex_max = exm;
 }
-__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+
+// Warp sums with the REDUX unit (one instruction per 32-bit reduction instead of five
+// shuffle + add steps).  The 64-bit form splits the value at bit 24: both halves of the
+// per-lane values summed here (bit costs, sums of zig-zag values over E samples) are far
+// below 2^51, so neither partial sum can wrap.
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) { return __reduce_add_sync(kFull, v); }
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+  const uint32_t lo = __reduce_add_sync(kFull, (uint32_t)v & 0xFFFFFFu);
+  const uint32_t hi = __reduce_add_sync(kFull, (uint32_t)(v >> 24));
+  return ((u64)hi << 24) + lo;
+}
+// full-width (wrapping) 64-bit warp sum, for values that use all 64 bits
+__device__ __forceinline__ u64 warp_sum_u64_full(u64 v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFull, v, d);
   return v;
@@ -297,6 +371,33 @@ __device__ __forceinline__ uint32_t best_static_k(u64 T0, const PlaneCounts& pc,
   }
   if (bits_out) *bits_out = best;
   return bk;
+}
+
+// The same argmin evaluated by a whole warp, one k per lane (every lane gets the result):
+// T_k = (T_0 - sum_{b<k} c_b 2^b) >> k, the subtracted sum being an exclusive prefix over the
+// lanes (below 2^30: a block has at most 2^14 samples and only planes 0..15 are counted).
+// `words` = the eight packed plane-count words.
+__device__ __forceinline__ uint32_t warp_best_static_k(u64 T0, const uint32_t* words, uint32_t cnt, int kmax,
+                                                       u64* bits_out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t c = lane < 16u ? ((words[lane >> 1] >> ((lane & 1u) * 16u)) & 0xFFFFu) : 0u;
+  const uint32_t part = lane < 16u ? (c << lane) : 0u;
+  uint32_t inc = part;
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(kFull, inc, d);
+    if (lane >= (uint32_t)d) inc += y;
+  }
+  const u64 T = (T0 - (u64)(inc - part)) >> (lane & 15u);
+  u64 key = ((T + (u64)cnt * (lane + 1u)) << 5) | lane;  // cost < 2^47
+  if (lane > (uint32_t)kmax) key = ~0ull;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const u64 y = __shfl_xor_sync(kFull, key, d);
+    if (y < key) key = y;
+  }
+  if (bits_out) *bits_out = key >> 5;
+  return (uint32_t)key & 31u;
 }
 
 }  // namespace lacb

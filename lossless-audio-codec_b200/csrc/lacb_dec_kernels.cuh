@@ -711,8 +711,8 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
       // taps 2..12 do not depend on the previous sample: only c1*h1 sits on the serial chain
       i64 acc = 0;
 #pragma unroll
-      for (int t = 2; t <= 12; ++t) acc += (i64)cf[t] * (i64)h[t];
-      acc += (i64)cf[1] * (i64)h[1];
+      for (int t = 2; t <= 12; ++t) acc = mad_wide(cf[t], h[t], acc);
+      acc = mad_wide(cf[1], h[1], acc);
       const i64 s = (acc >> 15) + (i64)val;
       if (s < -2147483648ll || s > 2147483647ll) return false;
       val = (int32_t)s;

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(NT) k_autocorr(PcmSrc src, const uint32_t* job
     }
 #pragma unroll
     for (int k = 0; k < 13; ++k) {
-      const u64 t = warp_sum_u64(s[k]);
+      const u64 t = warp_sum_u64_full(s[k]);  // products of int32 samples: all 64 bits in use
       if ((tid & 31u) == 0u) atomicAdd(&red[k], t);
     }
     __syncthreads();
@@ -299,12 +299,6 @@ __global__ void k_levinson(PcmSrc src, const uint32_t* jobs, const uint32_t* job
 
 // ---------------------------------------------------------------------------
 // K4+K7+K8+K9: channel-block analysis.
-struct BestCand {
-  u64 rice, zr, bin, stat, best;
-  uint32_t type, order, taps, ci, k_init, k_stat, has_run;
-  bool have;
-};
-
 template <int NT, int E>
 __device__ __forceinline__ u64 block_sum_u64(const ASmem<NT, E>& sm, u64 v) {
   AMisc* mi = sm.Misc();
@@ -351,10 +345,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
     const LpcQ* lq = lpcq + slot;
     if (!PROBE && tid < 11u) recs[slot].cand_lo[tid] = 0xFFFFFFFFu;
 
-    BestCand best;
-    best.have = false;
-    best.rice = best.zr = best.bin = best.stat = best.best = 0ull;
-    best.type = best.order = best.taps = best.ci = best.k_init = best.k_stat = best.has_run = 0u;
+    if (tid == 0u) mi->best.have = 0u;  // ordered before its first use by the barriers of the first candidate
     // candidate order: fixed 0..4, FIR, LPC 4,6,8,10,12 (block/encoder.cpp:362-407)
     for (uint32_t ci = 0; ci < 11u; ++ci) {
       int32_t r[E];
@@ -400,35 +391,29 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
       }
       Prep<NT, E> pr;
       prepare<NT, E, false>(sm, r, n, pr);
+      // initial / static k of the whole block: every warp evaluates them on its own (one k per
+      // lane) from the block totals, so no thread waits on a serial search
+      u64 stat;
+      const uint32_t k_init = warp_best_static_k(mi->p_first, mi->cnt_first, n < 256u ? n : 256u, 12, nullptr);
+      const uint32_t k_stat = warp_best_static_k(mi->u_total, mi->cnt_tot, n, 15, &stat);
+      const uint32_t has_run = cost_pass<NT, E, true>(sm, pr, n, 0u, k_init);
       if (tid == 0u) {
-        PlaneCounts pf, pt;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          pf.w[w] = mi->cnt_first[w];
-          pt.w[w] = mi->cnt_tot[w];
+        const u64 rice = mi->tot_rice, bin = mi->tot_bin;
+        const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
+        const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
+        const u64 bb = m1 < m2 ? m1 : m2;
+        if (!PROBE) recs[slot].cand_lo[ci] = (uint32_t)bb;
+        BestCand& best = mi->best;
+        if (!best.have || bb < best.best || (bb == best.best && type < best.type)) {  // :352-359
+          best.have = 1u;
+          best.rice = rice; best.zr = zr; best.bin = bin; best.stat = stat; best.best = bb;
+          best.type = type; best.order = order; best.taps = taps; best.ci = ci;
+          best.k_init = k_init; best.k_stat = k_stat; best.has_run = has_run;
         }
-        const uint32_t cnt = n < 256u ? n : 256u;
-        mi->k_init = best_static_k(mi->p_first, pf, cnt, 12, nullptr);
-        u64 sb;
-        mi->k_stat = best_static_k(mi->u_total, pt, n, 15, &sb);
-        mi->stat_bits = sb;
       }
-      __syncthreads();
-      cost_pass<NT, E, true>(sm, pr, n, 0u, mi->k_init);
-      const u64 rice = mi->tot_rice, bin = mi->tot_bin, stat = mi->stat_bits;
-      const uint32_t has_run = mi->has_run;
-      const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
-      const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
-      const u64 bb = m1 < m2 ? m1 : m2;
-      if (!PROBE && tid == 0u) recs[slot].cand_lo[ci] = (uint32_t)bb;
-      if (!best.have || bb < best.best || (bb == best.best && type < best.type)) {  // :352-359
-        best.have = true;
-        best.rice = rice; best.zr = zr; best.bin = bin; best.stat = stat; best.best = bb;
-        best.type = type; best.order = order; best.taps = taps; best.ci = ci;
-        best.k_init = mi->k_init; best.k_stat = mi->k_stat; best.has_run = has_run;
-      }
-      __syncthreads();
     }
+    __syncthreads();
+    const BestCand best = mi->best;
 
     // winner residual again, with the full prefix structures for the partition search
     const int16_t* wcoef = best.type == PRED_LPC ? lq->coef[best.ci - 6u] : nullptr;

@@ -62,7 +62,15 @@ __device__ __forceinline__ uint32_t max_partition_order(uint32_t n) {
   return mp;
 }
 
+// Best predictor candidate so far (block-uniform; kept in shared memory, thread 0 updates it).
+struct BestCand {
+  u64 rice, zr, bin, stat, best;
+  uint32_t type, order, taps, ci, k_init, k_stat, has_run;
+  uint32_t have;
+};
+
 struct AMisc {
+  BestCand best;
   u64 tot_rice, tot_zr, tot_bin, u_total, p_first, stat_bits, red64;
   uint32_t cnt_tot[8], cnt_first[8];
   uint32_t k_init, k_stat, has_run, red32;
@@ -80,7 +88,7 @@ struct ASmem {
   static constexpr size_t oFlg = oCpre + (size_t)(NT + 1) * 32;
   static constexpr size_t oKpub = oFlg + (size_t)NT * 4;
   static constexpr size_t oScr = oKpub + (size_t)NT * E;
-  static constexpr size_t oSegP = oScr + 40 * 8;
+  static constexpr size_t oSegP = oScr + 64 * 8;
   static constexpr size_t oSegStat = oSegP + (MAXSEG + 1) * 8;
   static constexpr size_t oSelBits = oSegStat + (MAXSEG + 1) * 8;
   static constexpr size_t oFb = oSelBits + (MAXSEG + 1) * 8;
@@ -181,7 +189,7 @@ __device__ __forceinline__ bool residual_lpc_t(const int32_t (&x)[E + 12], uint3
   for (int j = 0; j < E; ++j) {
     i64 acc = 0;
 #pragma unroll
-    for (int t = 1; t <= TAPS; ++t) acc += (i64)cf[t] * (i64)x[12 + j - t];
+    for (int t = 1; t <= TAPS; ++t) acc = mad_wide(cf[t], x[12 + j - t], acc);
     const i64 d = (i64)x[12 + j] - (acc >> 15);
     const bool in = g0 + j < n;
     if (in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
@@ -207,7 +215,7 @@ __device__ __forceinline__ bool residual_lpc(const int32_t (&x)[E + 12], uint32_
     i64 acc = 0;
 #pragma unroll
     for (int t = 1; t <= 12; ++t)
-      if (t <= taps) acc += (i64)c[t] * (i64)x[12 + j - t];
+      if (t <= taps) acc = mad_wide((int32_t)c[t], x[12 + j - t], acc);
     const i64 d = (i64)x[12 + j] - (acc >> 15);
     const bool in = g0 + j < n;
     if (in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
@@ -228,6 +236,7 @@ struct Prep {
   int32_t lnz_ex;   // index of the last non-zero residual before the chunk (-1: none)
   uint32_t zmask;   // bit j: sample g0+j exists and its residual is zero
   uint32_t any4;    // block-uniform: the residual contains a run of >= 4 zeros somewhere
+  uint32_t cls;     // bit 0: some sample of the chunk has u <= 4; bits 8..13: bit width of the OR of the chunk's u
 };
 
 template <int NT, int E>
@@ -250,17 +259,20 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   uint32_t u[E];
   u64 S = 0;
   int32_t lastnz = -1;
-  uint32_t zmask = 0;
+  uint32_t zmask = 0, umin = 0xFFFFFFFFu, uor = 0u;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const bool in = g0 + j < n;
     const uint32_t uu = in ? zz32(r[j]) : 0u;
     u[j] = uu;
     S += uu;
+    uor |= uu;
+    if (in && uu < umin) umin = uu;
     if (uu) lastnz = (int32_t)(g0 + j);
     if (in && uu == 0u) zmask |= 1u << j;
   }
   pr.zmask = zmask;
+  pr.cls = (umin <= 4u ? 1u : 0u) | ((32u - (uint32_t)__clz((int)uor)) << 8);
   uint4* U4 = reinterpret_cast<uint4*>(sm.U());
 #pragma unroll
   for (int c = 0; c < E / 4; ++c)
@@ -271,9 +283,10 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   }
   uint32_t V[5];
   csa_count<E>(u, V);
-  __syncthreads();
+  // one pass: prefix of u and index of the last non-zero residual before the chunk.  Its
+  // barrier also orders the U plane and the zeroed counters before everything below.
   u64 total;
-  pr.Pex = block_excl_scan_u64<NT>(S, sm.Scr(), &total);
+  block_scan_sum_max<NT, FULL>(S, lastnz, sm.Scr(), &pr.Pex, &total, &pr.lnz_ex);
   sm.Pthr()[tid] = pr.Pex;
   if (tid == 0) {
     sm.Pthr()[NT] = total;
@@ -281,12 +294,11 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     if (NT * E <= 256) mi->p_first = total;
   }
   if (NT * E > 256 && g0 == 256u) mi->p_first = pr.Pex;
-  pr.lnz_ex = block_excl_max_i32<NT>(lastnz, reinterpret_cast<int32_t*>(sm.Scr()));
 
   PlaneCounts pc;
 #ifdef LACB_X_NOPREP
   for (int w = 0; w < 8; ++w) pc.w[w] = V[w % 5];
-  if (!FULL) { __syncthreads(); pr.any4 = 0u; return; }
+  if (!FULL) { pr.any4 = (uint32_t)__syncthreads_or(0); return; }
 #else
   planes_from_sliced(V, pc);
 #endif
@@ -311,7 +323,6 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
       }
     }
   }
-  __syncthreads();
   {
     // any run of >= 4 zeros starting inside this chunk (look-ahead reaches 4 samples into the
     // next chunk)?  Without one, no partition of any level can use a zero-run token and all
@@ -438,15 +449,32 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
   flg_out = flg;
 }
 
+// 4 mask bits -> 4 bytes of 0 / 1
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t m) { return ((m & 0xFu) * 0x00204081u) & 0x01010101u; }
+// 0x01 in every byte of a packed k word (bytes <= 31) that is not zero
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) { return ((w + 0x7F7F7F7Fu) >> 7) & 0x01010101u; }
+
+// Bias of the stateful model (Rice::adapt_k, rice.hpp:60-112) on top of the base k series.
+//
+// Most chunks never need the per-sample recurrences:
+//  * drift rule (256-sample window mean against the running mean): with the window sum
+//    bounded by [W0 - S_leave, W0 + S_own] and (N, c) bounded by their values at the two
+//    ends of the chunk, one pair of comparisons proves the rule yields the same value
+//    (0, +1 or -1) for all E samples;
+//  * micro rule (flags of the last 96 samples): the counts at the start of the chunk are
+//    exact sums of whole threads' flag words; the "large" rule is decided for the whole
+//    chunk by its extreme counts, the "zero" rule, which hovers around its threshold on
+//    stationary signals, by a 16-step count over two flag words.
+// The bias is then applied to the four packed k words with byte-parallel arithmetic.
+// Chunks where a bound fails (level changes, block start) run the exact per-sample loop.
 template <int NT, int E, bool FAST>
 __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t flg,
                                               uint32_t (&kpk)[E / 4]) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
-  uint32_t u[E];
-  load_u<NT, E>(sm, u);
   const uint32_t* Flg = sm.Flg();
   constexpr int D = (int)kMicroWin / E;       // threads spanned by the 96-sample micro window
   constexpr int DW = (int)kDriftWin / E;      // threads spanned by the 256-sample drift window
+  static_assert(E <= 16, "flag words hold 16 + 16 bits");
   uint32_t fullL = 0u, fullZ = 0u;
 #pragma unroll
   for (int d = 1; d < D; ++d) {
@@ -460,32 +488,90 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
 #ifdef LACB_X_NOBIAS
   return;
 #endif
+  const uint32_t c_first = g0 + 1u, c_last = g0 + (uint32_t)E;
+  // exact window counts over the 96 samples before item 0
+  const uint32_t L0 = fullL + (uint32_t)__popc(part & 0xFFFFu), Z0 = fullZ + (uint32_t)__popc(part >> 16);
   {
-    // Cheap proof that every bias in this chunk is 0 (then the k series is the base series):
-    //  * micro window: even counting every flag of the 7 threads it can touch, neither
-    //    count reaches its threshold;
-    //  * drift window: with lm bounded by [W0 - S_leave, W0 + S_own] and (N, c) bounded as in
-    //    the k shortcut, neither comparison can fire.
-    const uint32_t c_first = g0 + 1u, c_last = g0 + (uint32_t)E;
-    const uint32_t Lub = fullL + (uint32_t)__popc(part & 0xFFFFu) + (uint32_t)__popc(flg & 0xFFFFu);
-    const uint32_t Zub = fullZ + (uint32_t)__popc(part >> 16) + (uint32_t)__popc(flg >> 16);
-    bool quiet = !(c_last >= kMicroWin && (Lub * 4u >= 288u || Zub * 5u >= 384u));
-    if (quiet && c_last >= kDriftWin) {
-      const u64 S_own = sm.Pthr()[tid + 1u] - pr.Pex;
-      const u64 S_leave = tt >= 0 ? sm.Pthr()[tt + 1] - sm.Pthr()[tt] : 0ull;
-      const u64 W0 = pr.Pex - wprev;
-      const u64 lm_max = (W0 + S_own + 128ull) >> 8, lm_min = (W0 - S_leave + 128ull) >> 8;
-      const u64 N_first = pr.Pex + u[0] + (c_first >> 1), N_last = pr.Pex + S_own + (c_last >> 1);
-      const u64 tA = (3ull * lm_max + 3ull) >> 2, tB = lm_min + 2ull + lm_min / 3ull;
-      quiet = (N_first >= tA * c_last) && (N_last < tB * c_first);
+    bool hard = false;
+    int drift = 0;
+    if (c_last >= kDriftWin) {
+      if (c_first < kDriftWin || tt < 0) {
+        hard = true;  // the rule switches on inside this chunk
+      } else {
+        const u64 S_own = sm.Pthr()[tid + 1u] - pr.Pex;
+        const u64 S_leave = sm.Pthr()[tt + 1] - wprev;
+        const u64 W0 = pr.Pex - wprev;
+        const u64 lm_max = (W0 + S_own + 128ull) >> 8, lm_min = (W0 - S_leave + 128ull) >> 8;
+        const u64 N_lo = pr.Pex + (c_first >> 1), N_hi = pr.Pex + S_own + (c_last >> 1);
+        const u64 tA_max = (3ull * lm_max + 3ull) >> 2, tB_min = lm_min + 2ull + lm_min / 3ull;
+        if (N_lo >= tA_max * c_last && N_hi < tB_min * c_first) {
+          drift = 0;
+        } else {
+          const u64 tA_min = (3ull * lm_min + 3ull) >> 2, tB_max = lm_max + 2ull + lm_max / 3ull;
+          if (N_hi < tA_min * c_first && N_lo >= (u64)c_last) drift = 1;
+          else if (N_lo >= tB_max * c_last) drift = -1;
+          else hard = true;
+        }
+      }
     }
-    if (quiet) return;
+    bool l_on = false;
+    uint32_t mz = 0u;  // samples where the zero rule fires (and the large rule does not)
+    if (!hard && c_last >= kMicroWin) {
+      if (c_first < kMicroWin) {
+        hard = true;
+      } else {
+        const uint32_t fl = flg & 0xFFFFu, fz = flg >> 16, pl = part & 0xFFFFu, pz = part >> 16;
+        if (L0 + (uint32_t)__popc(fl) < 72u) l_on = false;
+        else if (L0 >= 72u + (uint32_t)__popc(pl)) l_on = true;
+        else hard = true;
+        if (!hard && !l_on) {
+          if (Z0 + (uint32_t)__popc(fz) < 77u) {
+            mz = 0u;
+          } else if (Z0 >= 77u + (uint32_t)__popc(pz)) {
+            mz = 0xFFFFu;
+          } else {
+            uint32_t z = Z0;
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+              z += ((fz >> j) & 1u) - ((pz >> j) & 1u);
+              mz |= (z >= 77u ? 1u : 0u) << j;
+            }
+          }
+        }
+      }
+    }
+    if (!hard) {
+      // bias = uniform part bu, minus one where dm is set
+      int bu;
+      uint32_t dm;
+      if (l_on) { bu = drift + 1 < 1 ? drift + 1 : 1; dm = 0u; }
+      else if (drift < 0) { bu = -1; dm = 0u; }
+      else { bu = drift; dm = mz; }
+      if (bu > 0) {
+        // k + 1 must stay <= 31 in every byte, else the exact loop does the clamping
+#pragma unroll
+        for (int c4 = 0; c4 < E / 4; ++c4) hard = hard || (((kpk[c4] + 0x61616161u) & 0x80808080u) != 0u);
+      }
+      if (!hard) {
+#pragma unroll
+        for (int c4 = 0; c4 < E / 4; ++c4) {
+          uint32_t w = kpk[c4];
+          if (bu > 0) w += 0x01010101u;
+          else if (bu < 0) w -= nonzero_bytes(w);
+          if (dm) w -= expand_nibble(dm >> (4 * c4)) & nonzero_bytes(w);
+          kpk[c4] = w;
+        }
+        return;
+      }
+    }
   }
+  uint32_t u[E];
+  load_u<NT, E>(sm, u);
   const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
   u64 Pin = pr.Pex;
   uint32_t uw[4] = {0u, 0u, 0u, 0u};
   // sliding micro-window counts: start with the window that ends just before item 0
-  uint32_t L = fullL + (uint32_t)__popc(part & 0xFFFFu), Z = fullZ + (uint32_t)__popc(part >> 16);
+  uint32_t L = L0, Z = Z0;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const uint32_t c = g0 + j + 1u;
@@ -655,8 +741,8 @@ __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT
 // block totals to AMisc; otherwise per-segment prefix values go to Fb (3 x 258) and
 // the has-run bits to AMisc::hasrun_bits.
 template <int NT, int E, bool STATEFUL>
-__device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t p,
-                                          uint32_t kinit_stateful) {
+__device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t p,
+                                              uint32_t kinit_stateful) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
   AMisc* mi = sm.Misc();
   const SegGeom sg = seg_geom<E>(g0, n, STATEFUL ? 0u : p);
@@ -676,6 +762,43 @@ __device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT,
   }
   u64 riceA = 0, zrA = 0, binA = 0, riceB = 0, zrB = 0, binB = 0;
   uint32_t runA = 0, runB = 0;
+  // Plain chunks -- all E samples in one segment, every u > 4 (so no zero, no +-1/+-2 bin code)
+  // and below 2^24 -- cost rice = sum (u >> k) + k + 1 per sample, and the other two modes
+  // exactly two bits more per sample unless a zero-run escape (u > 8 << k, i.e. some q >= 8
+  // here) can occur; those and all other chunks take the general walk.
+  bool plain = sg.fast && !(pr.cls & 1u) && (pr.cls >> 8) <= 24u;
+#ifdef LACB_X_NOWALK
+  plain = false;
+#endif
+  if (plain) {
+    uint32_t u[E];
+    load_u<NT, E>(sm, u);
+    const uint32_t* K = sm.Kpl() + tid * (E / 4);
+    uint32_t kprev = tid ? (K[-1] >> 24) : 0u;
+    if (g0 == sg.a0) kprev = kinitA;
+    uint32_t acc = 0u, qor = 0u, ksum = 0u;  // acc is only used when every q < 8
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) {
+      const uint32_t kw = K[c4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int j = 4 * c4 + b;
+        const uint32_t k = kprev;
+        kprev = (kw >> (8 * b)) & 0xFFu;
+        const uint32_t q = (k >= 31u) ? 0u : (u[j] >> k);
+        qor |= q;
+        acc += q;
+        ksum += k;
+      }
+    }
+    if (qor < 8u) {
+      riceA = (u64)(acc + ksum + (uint32_t)E);
+      zrA = binA = riceA + 2ull * (uint32_t)E;
+    } else {
+      plain = false;
+    }
+  }
+  if (!plain)
   walk_items<NT, E>(sm, pr, n, sg, kinitA, kinitB,
                     [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
                         bool long_run) {
@@ -704,9 +827,7 @@ __device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT,
       atomicAdd(&mi->tot_zr, z);
       atomicAdd(&mi->tot_bin, b);
     }
-    const int any = __syncthreads_or((int)runA);
-    if (tid == 0) mi->has_run = (uint32_t)any;
-    __syncthreads();
+    return (uint32_t)__syncthreads_or((int)runA);  // also publishes the totals
   } else {
     u64* Fb = sm.Fb();
     const uint32_t cnt = 1u << p;
@@ -728,6 +849,7 @@ __device__ __forceinline__ void cost_pass(const ASmem<NT, E>& sm, const Prep<NT,
     if (runA) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
     if (runB) atomicOr(&mi->hasrun_bits[(sg.s0 + 1u) >> 5], 1u << ((sg.s0 + 1u) & 31u));
     __syncthreads();
+    return 0u;
   }
 }
 

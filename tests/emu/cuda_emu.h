@@ -224,6 +224,29 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     if (((mask >> i) & 1u) && s[i]) r |= 1u << i;
   return r;
 }
+// warp reductions (REDUX on sm_80+): every existing lane named in the mask contributes
+static inline unsigned emu_reduce(unsigned mask, unsigned v, int op) {
+  const uint64_t* s = emu::warp_exchange(mask, (uint64_t)v);
+  emu::Block& b = *emu::g_block;
+  const unsigned wbase = emu::g_cur->tid & ~31u;
+  const unsigned lanes = std::min(32u, b.nthreads - wbase);
+  unsigned r = op == 2 ? 0u : 0u;
+  bool first = true;
+  for (unsigned i = 0; i < lanes; ++i) {
+    if (!((mask >> i) & 1u)) continue;
+    const unsigned x = (unsigned)s[i];
+    if (first) { r = x; first = false; continue; }
+    if (op == 0) r += x;
+    else if (op == 1) r |= x;
+    else if (op == 2) r = x > r ? x : r;
+    else r = x < r ? x : r;
+  }
+  return r;
+}
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return emu_reduce(mask, v, 0); }
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return emu_reduce(mask, v, 1); }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu_reduce(mask, v, 2); }
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return emu_reduce(mask, v, 3); }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) {
   emu::Block& b = *emu::g_block;
