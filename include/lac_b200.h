@@ -153,7 +153,8 @@ typedef struct lacb_block_info {
   uint32_t predictor_type, order, partition_order, n_parts, taps;
   int16_t coeffs[13];
   uint8_t part_mode[256], part_k[256];
-  uint32_t cand_best_lo[11];
+  uint32_t cand_best_lo[11]; /* low 32 bits of each candidate's best cost; 0xFFFFFFFF = not applicable,
+                                0xFFFFFFFE = dropped early: its lower bound exceeded the best cost so far */
   uint32_t bits;
 } lacb_block_info;
 int lacb_last_block_info(lacb_ctx* ctx, lacb_block_info* info);

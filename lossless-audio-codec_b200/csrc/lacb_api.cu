@@ -316,6 +316,19 @@ void lacb_destroy(lacb_ctx* ctx) {
 
 const char* lacb_last_error(const lacb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
 void lacb_free(void* p) { free(p); }
+#if defined(LACB_PHASE_CLK) && !defined(LACB_EMU)
+// debug builds only (tools/phase_clk.py): copies out and optionally clears the phase clock table
+int lacb_debug_phase_clk(unsigned long long* out64, int reset) {
+  cudaDeviceSynchronize();
+  if (out64 && cudaMemcpyFromSymbol(out64, lacb::g_phase_clk, 64 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(lacb::g_phase_clk, z, sizeof z);
+  }
+  return 0;
+}
+#endif
+
 int lacb_get_timing(const lacb_ctx* ctx, lacb_timing* out) {
   if (!ctx || !out) return LACB_EINVAL;
   *out = ctx->timing;

@@ -37,6 +37,35 @@ constexpr uint32_t kFull = 0xFFFFFFFFu;
 typedef unsigned long long u64;
 typedef long long i64;
 
+// Optional phase clocks (-DLACB_PHASE_CLK, tools/phase_clk.py): cycles every warp spends in
+// each numbered phase of k_analyze, accumulated in a global table.  Compiled out of the product.
+#if defined(LACB_PHASE_CLK) && !defined(LACB_EMU)
+__device__ unsigned long long g_phase_clk[64];
+struct PhState { long long last[32]; int base; };
+__device__ __forceinline__ PhState* ph_state() { __shared__ PhState st; return &st; }
+__device__ __forceinline__ void ph_init(int base) {
+  PhState* st = ph_state();
+  if ((threadIdx.x & 31u) == 0u) st->last[threadIdx.x >> 5] = clock64();
+  if (threadIdx.x == 0u) st->base = base;
+}
+__device__ __forceinline__ void ph_base(int base) { if (threadIdx.x == 0u) ph_state()->base = base; }
+__device__ __forceinline__ void ph_mark(int id) {
+  PhState* st = ph_state();
+  if ((threadIdx.x & 31u) == 0u && st->base >= 0) {
+    const long long t = clock64();
+    atomicAdd(&g_phase_clk[st->base + id], (unsigned long long)(t - st->last[threadIdx.x >> 5]));
+    st->last[threadIdx.x >> 5] = t;
+  }
+}
+#define LACB_PH_INIT(b) ph_init(b)
+#define LACB_PH_BASE(b) ph_base(b)
+#define LACB_PH(id) ph_mark(id)
+#else
+#define LACB_PH_INIT(b)
+#define LACB_PH_BASE(b)
+#define LACB_PH(id)
+#endif
+
 // zig-zag, block/encoder.cpp:61-65 and rice/rice.cpp:7-15
 __device__ __forceinline__ uint32_t zz32(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
 __device__ __forceinline__ int32_t unzz32(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1u); }
@@ -96,6 +125,14 @@ __device__ __forceinline__ uint32_t kbase_clz(u64 N, uint32_t c) {
   const uint32_t t = (uint32_t)(M >> s0);
   const uint32_t kb = 1u + s0 - (t < c ? 1u : 0u);
   return kb > 31u ? 31u : kb;
+}
+
+// the same for N < 2^31 (sums of a whole block of 24-bit audio residuals stay far below), all 32-bit
+__device__ __forceinline__ uint32_t kbase_clz32(uint32_t N, uint32_t c) {
+  if (N < 2u * c) return 0u;
+  const uint32_t M = N - c;
+  const uint32_t s0 = (uint32_t)__clz((int)c) - (uint32_t)__clz((int)M);  // bit_width(M) - bit_width(c), M >= c
+  return 1u + s0 - ((M >> s0) < c ? 1u : 0u);                             // <= 31 because M < 2^31
 }
 
 // rice_bits_for_unsigned, block/encoder.cpp:67-70
@@ -227,7 +264,9 @@ __device__ __forceinline__ void block_scan_sum_max(u64 v, int32_t m, u64* scratc
     scratch[w] = inc;
     smax[w] = im;
   }
+  LACB_PH(2);
   __syncthreads();
+  LACB_PH(3);
   u64 ws = (lane < (uint32_t)NW) ? scratch[lane] : 0ull;
   int32_t wm = (lane < (uint32_t)NW) ? smax[lane] : -1;
 #pragma unroll

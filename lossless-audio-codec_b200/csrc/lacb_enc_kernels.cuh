@@ -323,7 +323,7 @@ __device__ __forceinline__ bool compute_residual(const int32_t (&x)[E + 12], uin
     residual_fir<E>(x, g0, n, r);
     return false;
   }
-  return residual_lpc<E>(x, g0, n, coef, (int)taps, r);
+  return residual_lpc<E, false>(x, g0, n, coef, (int)taps, r);  // the analysis already settled the taps
 }
 
 template <int NT, int E, bool PROBE>
@@ -339,8 +339,11 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
     JobDesc jd;
     job_desc<PROBE>(src, slot, jd);
     const uint32_t n = jd.n;
-    load_block<NT, E>(sm, src, jd.kind, jd.start, n);
-    __syncthreads();
+    LACB_PH_INIT(PROBE ? -1 : 0);
+    // block-uniform: some sample needs more than 26 magnitude bits (never true for 16 / 24-bit audio);
+    // only then can an LPC residual leave int32 (lpc.cpp:38-61) and the fallback orders matter
+    const bool xbig = __syncthreads_or((int)((load_block<NT, E>(sm, src, jd.kind, jd.start, n) >> 26) != 0u)) != 0;
+    LACB_PH(0);
     const uint32_t max_valid = n > 1u ? (n - 1u < 32u ? n - 1u : 32u) : 0u;
     const LpcQ* lq = lpcq + slot;
     if (!PROBE && tid < 11u) recs[slot].cand_lo[tid] = 0xFFFFFFFFu;
@@ -372,8 +375,13 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
         order = co;
         // compute_residual_q15 attempts (lpc.cpp:188-229): used, then {12,10,8,6,4} below it
         uint32_t attempt = used < co ? used : co;
+        if (!xbig) {
+          residual_lpc<E, false>(x, g0, n, lq->coef[c], (int)attempt, r);
+          taps = attempt;
+          attempt = 0u;
+        }
         while (attempt > 0u) {
-          const bool ovf = residual_lpc<E>(x, g0, n, lq->coef[c], (int)attempt, r);
+          const bool ovf = residual_lpc<E, true>(x, g0, n, lq->coef[c], (int)attempt, r);
           if (!__syncthreads_or((int)ovf)) {
             taps = attempt;
             break;
@@ -390,7 +398,16 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
       }
       }
       Prep<NT, E> pr;
+      LACB_PH(1);
       prepare<NT, E, false>(sm, r, n, pr);
+#ifndef LACB_X_NOPRUNE
+      if (mi->best.have && (u64)mi->lb > mi->best.best) {
+        // cannot beat (or tie) the best candidate so far: skip its adaptive-k evaluation
+        if (!PROBE && tid == 0u) recs[slot].cand_lo[ci] = 0xFFFFFFFEu;
+        __syncthreads();  // everyone has read lb / best before the next candidate resets them
+        continue;
+      }
+#endif
       // initial / static k of the whole block: every warp evaluates them on its own (one k per
       // lane) from the block totals, so no thread waits on a serial search
       u64 stat;
@@ -412,7 +429,9 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
         }
       }
     }
+    LACB_PH(1);
     __syncthreads();
+    LACB_PH_BASE(PROBE ? -1 : 20);
     const BestCand best = mi->best;
 
     // winner residual again, with the full prefix structures for the partition search
@@ -424,6 +443,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
       compute_residual<NT, E>(x, g0, n, best.type, best.order, best.taps, wcoef, r);
     }
     Prep<NT, E> pr;
+    LACB_PH(1);
     prepare<NT, E, true>(sm, r, n, pr);
 
 #ifdef LACB_X_NOLEVELS
@@ -455,7 +475,9 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
       sm.SegStat()[sid] = sb;
       sm.SegK()[sid] = (uint16_t)(ki | (ks << 8));
     }
+    LACB_PH(12);
     __syncthreads();
+    LACB_PH(13);
 
     // base (p = 0) mode, block/encoder.cpp:432-484
     const bool allow_zr = cfg.zero_run && best.has_run;
@@ -499,6 +521,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
         best_total = total;
         best_p = p;
       }
+      LACB_PH(16);
     }
 
     // exact emitted size of the chosen configuration (same token function as the emitter)
@@ -522,7 +545,9 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
                           if (emit) tok_bits += (u64)t.hlen + t.q + t.tlen;
                         });
     }
+    LACB_PH(17);
     const u64 all_tok = block_sum_u64<NT, E>(sm, tok_bits);
+    LACB_PH(18);
     const u64 bits = 16ull + (best.type == PRED_LPC ? 16ull * chosen_order : 0ull) + 8ull + 7ull * nparts + all_tok;
     const u64 bytes = (bits + 7ull) >> 3;
 
@@ -641,6 +666,7 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
     if (ch == 1u) out_off += recs[(size_t)b * 4u + s0].bytes;
     if (flagged && ch == 0u && tid == 0u) payload[blk_off[b]] = (f & BF_CHOOSE_MS) ? 1 : 0;
 
+    LACB_PH_INIT(-1);
     load_block<NT, E>(sm, src, (int)(s0 + ch), (u64)b * kMaxBlock, n);
     __syncthreads();
     int32_t x[E + 12];

@@ -74,6 +74,7 @@ struct AMisc {
   u64 tot_rice, tot_zr, tot_bin, u_total, p_first, stat_bits, red64;
   uint32_t cnt_tot[8], cnt_first[8];
   uint32_t k_init, k_stat, has_run, red32;
+  uint32_t lb;  // lower bound of the candidate's cost (see prepare)
   uint32_t hasrun_bits[8];
 };
 
@@ -117,14 +118,17 @@ struct ASmem {
 // ---------------------------------------------------------------------------
 // load the channel-block into the swizzled X plane (zero padded to CAP)
 template <int NT, int E>
-__device__ __forceinline__ void load_block(const ASmem<NT, E>& sm, const PcmSrc& src, int kind, u64 start,
-                                           uint32_t n) {
+__device__ __forceinline__ uint32_t load_block(const ASmem<NT, E>& sm, const PcmSrc& src, int kind, u64 start,
+                                               uint32_t n) {
   int32_t* X = sm.X();
+  uint32_t mag = 0u;  // OR of the magnitudes (v >= 0 ? v : ~v) of the samples this thread loaded
   for (uint32_t i = threadIdx.x; i < ASmem<NT, E>::CAP; i += NT) {
     int32_t v = 0;
     if (i < n) v = load_sample(src, kind, start + i);
+    mag |= (uint32_t)(v ^ (v >> 31));
     X[swz(i)] = v;
   }
+  return mag;
 }
 
 // x[0..11] = the 12 samples before the thread's chunk (zero before the block start),
@@ -178,7 +182,9 @@ __device__ __forceinline__ void residual_fir(const int32_t (&x)[E + 12], uint32_
   }
 }
 // LPC residual with `TAPS` Q15 taps, lpc.cpp:38-61; returns true if any residual leaves int32
-template <int E, int TAPS>
+// CHECK = false: the caller knows every |x| < 2^26, so |x - (sum >> 15)| < 2^26 + 12 * 2^26 * 2^15 / 2^15 < 2^31
+// and the int32 range test of compute_residual_q15 cannot fire.
+template <int E, int TAPS, bool CHECK>
 __device__ __forceinline__ bool residual_lpc_t(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n,
                                                const int16_t* c, int32_t (&r)[E]) {
   int32_t cf[TAPS + 1];
@@ -192,20 +198,20 @@ __device__ __forceinline__ bool residual_lpc_t(const int32_t (&x)[E + 12], uint3
     for (int t = 1; t <= TAPS; ++t) acc = mad_wide(cf[t], x[12 + j - t], acc);
     const i64 d = (i64)x[12 + j] - (acc >> 15);
     const bool in = g0 + j < n;
-    if (in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
+    if (CHECK && in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
     r[j] = in ? (int32_t)d : 0;
   }
   return ovf;
 }
-template <int E>
+template <int E, bool CHECK = true>
 __device__ __forceinline__ bool residual_lpc(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n,
                                              const int16_t* c, int taps, int32_t (&r)[E]) {
   switch (taps) {
-    case 4: return residual_lpc_t<E, 4>(x, g0, n, c, r);
-    case 6: return residual_lpc_t<E, 6>(x, g0, n, c, r);
-    case 8: return residual_lpc_t<E, 8>(x, g0, n, c, r);
-    case 10: return residual_lpc_t<E, 10>(x, g0, n, c, r);
-    case 12: return residual_lpc_t<E, 12>(x, g0, n, c, r);
+    case 4: return residual_lpc_t<E, 4, CHECK>(x, g0, n, c, r);
+    case 6: return residual_lpc_t<E, 6, CHECK>(x, g0, n, c, r);
+    case 8: return residual_lpc_t<E, 8, CHECK>(x, g0, n, c, r);
+    case 10: return residual_lpc_t<E, 10, CHECK>(x, g0, n, c, r);
+    case 12: return residual_lpc_t<E, 12, CHECK>(x, g0, n, c, r);
     default: break;
   }
   // odd / short orders (Levinson stopped early): generic, coefficients past `taps` ignored
@@ -259,7 +265,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   uint32_t u[E];
   u64 S = 0;
   int32_t lastnz = -1;
-  uint32_t zmask = 0, umin = 0xFFFFFFFFu, uor = 0u;
+  uint32_t zmask = 0, umin = 0xFFFFFFFFu, uor = 0u, clzsum = 0u, n4 = 0u;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const bool in = g0 + j < n;
@@ -267,12 +273,31 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     u[j] = uu;
     S += uu;
     uor |= uu;
+    if (!FULL) {
+      clzsum += (uint32_t)__clz((int)uu);
+      n4 += uu == 4u ? 1u : 0u;
+    }
     if (in && uu < umin) umin = uu;
     if (uu) lastnz = (int32_t)(g0 + j);
     if (in && uu == 0u) zmask |= 1u << j;
   }
   pr.zmask = zmask;
   pr.cls = (umin <= 4u ? 1u : 0u) | ((32u - (uint32_t)__clz((int)uor)) << 8);
+  // Lower bound of what this residual can cost under ANY of the four coding modes, per sample:
+  // a Rice code of u takes at least bit_width(u) + 1 bits whatever k is (32 when u >= 2^31, where
+  // the k = 31 estimate drops the quotient); the bin code of u = 4 takes 3; a zero inside a
+  // zero run can be free; zero-run escapes and tags only add.  Candidates whose bound already
+  // exceeds the best exact cost so far are dropped before the expensive adaptive-k passes.
+  uint32_t lbt = 0u;
+  if (!FULL) {
+    const uint32_t inr = g0 >= n ? 0u : (n - g0 < (uint32_t)E ? n - g0 : (uint32_t)E);
+    lbt = 33u * (uint32_t)E - clzsum;                                // sum of bit_width(u) + 1, zeros counted as 1
+    lbt -= (uint32_t)__popc(zmask) + ((uint32_t)E - inr) + n4;       // zeros and missing samples: 0; u == 4: 3
+    if (uor >> 31) {
+#pragma unroll
+      for (int j = 0; j < E; ++j) lbt -= u[j] >> 31;
+    }
+  }
   uint4* U4 = reinterpret_cast<uint4*>(sm.U());
 #pragma unroll
   for (int c = 0; c < E / 4; ++c)
@@ -280,6 +305,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   if (!FULL && tid < 8) {
     mi->cnt_tot[tid] = 0u;
     mi->cnt_first[tid] = 0u;
+    if (tid == 0) mi->lb = 0u;
   }
   uint32_t V[5];
   csa_count<E>(u, V);
@@ -313,6 +339,10 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     }
   } else {
     const bool first = g0 < 256u;
+    {
+      const uint32_t t = warp_sum_u32(lbt);
+      if ((tid & 31u) == 0u && t) atomicAdd(&mi->lb, t);
+    }
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       const uint32_t t = warp_sum_u32(pc.w[w]);
@@ -329,7 +359,9 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     // run bookkeeping is skipped.
     const uint32_t zm = zero_lookahead(sm, pr, n);
     const uint32_t r4 = zm & (zm >> 1) & (zm >> 2) & (zm >> 3) & ((1u << E) - 1u);
+    LACB_PH(4);
     pr.any4 = (uint32_t)__syncthreads_or((int)(r4 != 0u));
+    LACB_PH(5);
   }
 }
 
@@ -430,6 +462,24 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
       flg_out = flg;
       return;
     }
+    if (N_last < 0x80000000ull) {
+      // k moves inside the chunk (block / segment start, level change): per-sample closed form,
+      // in 32-bit arithmetic when the running sum allows it
+      uint32_t N32 = (uint32_t)rel;
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        N32 += u[j];
+        const uint32_t c = c_first + (uint32_t)j;
+        const uint32_t kb = kbase_clz32(N32 + (c >> 1), c);
+        kpk[j >> 2] |= kb << (8 * (j & 3));
+        if (STATEFUL) {
+          const uint32_t q = u[j] >> kb;
+          flg |= ((q > 3u) ? (1u << j) : 0u) | ((q == 0u) ? (1u << (16 + j)) : 0u);
+        }
+      }
+      flg_out = flg;
+      return;
+    }
   }
 #pragma unroll
   for (int j = 0; j < E; ++j) {
@@ -494,9 +544,21 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
   {
     bool hard = false;
     int drift = 0;
+    // Chunks in which a rule switches on (sample counts 96 and 256 are multiples of E, so it
+    // switches on at the last sample): that one sample is evaluated exactly on its own.
+    bool patch_drift = false, patch_micro = false;
+    int drift_last = 0, micro_last = 0;
     if (c_last >= kDriftWin) {
-      if (c_first < kDriftWin || tt < 0) {
-        hard = true;  // the rule switches on inside this chunk
+      if (c_first < kDriftWin) {
+        patch_drift = true;  // c_last == 256: the window is everything so far
+        const u64 Pin = sm.Pthr()[tid + 1u];
+        const u64 N = Pin + (c_last >> 1);
+        if (N >= (u64)c_last) {
+          const u64 lm = (Pin - sm.Pthr()[tt + 1] + 128ull) >> 8;
+          const u64 tA = (3ull * lm + 3ull) >> 2, tB = lm + 2ull + lm / 3ull;
+          if (N < tA * c_last) drift_last = 1;
+          else if (N >= tB * c_last) drift_last = -1;
+        }
       } else {
         const u64 S_own = sm.Pthr()[tid + 1u] - pr.Pex;
         const u64 S_leave = sm.Pthr()[tt + 1] - wprev;
@@ -517,10 +579,13 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
     bool l_on = false;
     uint32_t mz = 0u;  // samples where the zero rule fires (and the large rule does not)
     if (!hard && c_last >= kMicroWin) {
+      const uint32_t fl = flg & 0xFFFFu, fz = flg >> 16, pl = part & 0xFFFFu, pz = part >> 16;
       if (c_first < kMicroWin) {
-        hard = true;
+        patch_micro = true;  // c_last == 96
+        const uint32_t Ll = L0 + (uint32_t)__popc(fl) - (uint32_t)__popc(pl);
+        const uint32_t Zl = Z0 + (uint32_t)__popc(fz) - (uint32_t)__popc(pz);
+        micro_last = Ll >= 72u ? 1 : (Zl >= 77u ? -1 : 0);
       } else {
-        const uint32_t fl = flg & 0xFFFFu, fz = flg >> 16, pl = part & 0xFFFFu, pz = part >> 16;
         if (L0 + (uint32_t)__popc(fl) < 72u) l_on = false;
         else if (L0 >= 72u + (uint32_t)__popc(pl)) l_on = true;
         else hard = true;
@@ -547,6 +612,7 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
       if (l_on) { bu = drift + 1 < 1 ? drift + 1 : 1; dm = 0u; }
       else if (drift < 0) { bu = -1; dm = 0u; }
       else { bu = drift; dm = mz; }
+      const uint32_t kb_last = kpk[E / 4 - 1] >> 24;
       if (bu > 0) {
         // k + 1 must stay <= 31 in every byte, else the exact loop does the clamping
 #pragma unroll
@@ -560,6 +626,19 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
           else if (bu < 0) w -= nonzero_bytes(w);
           if (dm) w -= expand_nibble(dm >> (4 * c4)) & nonzero_bytes(w);
           kpk[c4] = w;
+        }
+        if (patch_drift || patch_micro) {
+          int b;
+          if (patch_micro) {
+            b = micro_last;  // the drift rule is still off at sample 96
+          } else {
+            const bool z_last = (mz >> (E - 1)) & 1u;
+            b = l_on ? (drift_last + 1 < 1 ? drift_last + 1 : 1)
+                     : (z_last ? (drift_last - 1 > -1 ? drift_last - 1 : -1) : drift_last);
+          }
+          int k = (int)kb_last + b;
+          k = k < 0 ? 0 : (k > 31 ? 31 : k);
+          kpk[E / 4 - 1] = (kpk[E / 4 - 1] & 0x00FFFFFFu) | ((uint32_t)k << 24);
         }
         return;
       }
@@ -619,13 +698,17 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
   else k_series_thread<NT, E, STATEFUL, false>(sm, pr, n, sg, kpk, flg);
   if (STATEFUL) {
     sm.Flg()[tid] = flg;
+    LACB_PH(6);
     __syncthreads();
+    LACB_PH(7);
     k_bias_thread<NT, E, true>(sm, pr, flg, kpk);
   }
   uint32_t* K = sm.Kpl() + tid * (E / 4);
 #pragma unroll
   for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];
+  LACB_PH(8);
   __syncthreads();
+  LACB_PH(9);
 }
 
 // Zero mask of the thread's E samples plus the next 4 (look-ahead for run detection),
@@ -827,11 +910,15 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
       atomicAdd(&mi->tot_zr, z);
       atomicAdd(&mi->tot_bin, b);
     }
-    return (uint32_t)__syncthreads_or((int)runA);  // also publishes the totals
+    LACB_PH(10);
+    const uint32_t any_run = (uint32_t)__syncthreads_or((int)runA);  // also publishes the totals
+    LACB_PH(11);
+    return any_run;
   } else {
     u64* Fb = sm.Fb();
     const uint32_t cnt = 1u << p;
     u64 tot;
+    LACB_PH(10);
     const bool ownsA = (sg.a0 == g0);                                  // segment starts exactly at this thread
     const bool ownsB = (sg.bnd != 0xFFFFFFFFu && sg.bnd - g0 < (uint32_t)E && sg.bnd > g0);
     u64 ex = block_excl_scan_u64<NT>(riceA + riceB, sm.Scr(), &tot);
@@ -848,7 +935,9 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     if (tid == 0) Fb[516 + cnt] = tot;
     if (runA) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
     if (runB) atomicOr(&mi->hasrun_bits[(sg.s0 + 1u) >> 5], 1u << ((sg.s0 + 1u) & 31u));
+    LACB_PH(14);
     __syncthreads();
+    LACB_PH(15);
     return 0u;
   }
 }

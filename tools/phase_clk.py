@@ -1,0 +1,24 @@
+"""Per-phase warp cycles of k_analyze from a -DLACB_PHASE_CLK build of the library (debug aid).
+usage: phase_clk.py build/var/lib_PHASE.so [seconds]"""
+import ctypes as C, sys
+sys.path.insert(0, "tests")
+import numpy as np, helpers as H
+lib = sys.argv[1]; secs = int(sys.argv[2]) if len(sys.argv) > 2 else 120
+cd = H.lacb_module().Codec(0, lib)
+dll = C.CDLL(lib)
+l, r, pk = H.synth(2, 96000 * secs, 24, want_packed=True)
+buf = (C.c_ulonglong * 64)()
+cd.encode_blocks(None, None, 24, 1, packed=pk, channels=2)
+dll.lacb_debug_phase_clk(buf, 1)
+cd.encode_blocks(None, None, 24, 1, packed=pk, channels=2)
+dll.lacb_debug_phase_clk(buf, 1)
+v = np.array(buf[:], dtype=np.float64)
+tot = v.sum()
+names = {0: "load_block", 1: "residual(+loop top)", 2: "prepare->scan", 3: "wait scan", 4: "prepare rest", 5: "wait any4",
+         6: "static k + kbase/flags", 7: "wait flg", 8: "bias / k store", 9: "wait K", 10: "walk+reduce", 11: "wait totals",
+         12: "seg tables", 13: "wait seg", 14: "level scans", 15: "wait level", 16: "level select", 17: "final size", 18: "final sum"}
+print("analyze_ms", cd.timing()["analyze_ms"])
+for base, tag in ((0, "candidates"), (20, "levels/final")):
+    for i in range(20):
+        if v[base + i]:
+            print(f"{tag:13s} {i:2d} {names.get(i, ''):24s} {100 * v[base + i] / tot:6.2f}%")
