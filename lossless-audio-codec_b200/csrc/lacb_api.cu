@@ -244,13 +244,14 @@ __global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, uint32_t
   __shared__ uint32_t ring[kDriftWin];
   __shared__ ChanHdr hdr;
   __shared__ ParseScratch sc;
+  __shared__ int4 stage1[2 * kRestoreDepth];
   const uint32_t lane = threadIdx.x & 31u;
   BitRd r;
   rd_init(r, data, size, data + padded);
   bool ok = parse_channel_block(r, n, out, &hdr, ring, &sc, lane);
   __syncwarp();
   if (lane != 0u) return;
-  if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef);
+  if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef, stage1, 1u);
   result[0] = ok ? 1ull : 0ull;
   result[1] = ok ? rd_pos(r) - r.start : 0ull;
 }

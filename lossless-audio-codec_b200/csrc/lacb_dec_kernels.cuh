@@ -283,8 +283,10 @@ struct ChanHdr {
 
 // Per-warp scratch of the speculative token batches.
 struct ParseScratch {
-  uint32_t ring[128];  // big-endian words of the bitstream, slot = word index & 127
-  uint32_t tp[34];     // bit offset of every token of the batch from the word-aligned batch base; [cnt] = end
+  // big-endian words of the bitstream as overlapped pairs: ring[i & 127] = (word i) << 32 | word i+1,
+  // so the 32 bits at any bit position come from one 64-bit load and one funnel shift
+  u64 ring[128];
+  uint32_t tp[34];  // ring bit position of every token of the batch; [cnt] = end
 };
 // staged word range [lo, hi) of the ring (warp-uniform registers)
 struct Stage {
@@ -299,17 +301,22 @@ __device__ __forceinline__ void stage_ensure(const BitRd& r, ParseScratch* sc, S
   if (wi < sg.lo || wi > sg.hi) sg.lo = sg.hi = wi;  // outside the staged range: start over
   bool any = false;
   while (sg.hi < wi + 64u) {  // the slots overwritten hold words below wi - 32
-    sc->ring[(sg.hi + lane) & 127u] = rd_word(r, sg.hi + lane);
+    const uint32_t i = sg.hi + lane;
+    const uint32_t w0 = rd_word(r, i);
+    uint32_t w1 = __shfl_down_sync(kFull, w0, 1);
+    if (lane == 31u) w1 = rd_word(r, i + 1u);
+    sc->ring[i & 127u] = ((u64)w0 << 32) | w1;
     sg.hi += 32u;
     any = true;
   }
   if (sg.hi - sg.lo > 128u) sg.lo = sg.hi - 128u;
   if (any) __syncwarp();
 }
-// 32 bits from bit `rel` after word `wbase`
-__device__ __forceinline__ uint32_t ring_peek(const uint32_t* ring, uint32_t wbase, uint32_t rel) {
-  const uint32_t wi = wbase + (rel >> 5);
-  return __funnelshift_l(ring[(wi + 1u) & 127u], ring[wi & 127u], rel);
+// Ring bit positions: rp = ((word index & 127) << 5) + bit, allowed to run past 4096 (the slot
+// index wraps in the address).  32 bits starting at ring position rp:
+__device__ __forceinline__ uint32_t ring_peek(const u64* ring, uint32_t rp) {
+  const u64 v = ring[(rp >> 5) & 127u];
+  return __funnelshift_l((uint32_t)v, (uint32_t)(v >> 32), rp);
 }
 
 // One token by the exact serial reader (lane 0 only): value u, sample count w.
@@ -341,22 +348,22 @@ __device__ __forceinline__ bool parse_token(BitRd& r, uint32_t mode, uint32_t k,
 // 2-word window from the ring, a count-leading-ones and an add sit on the serial chain.
 // Stops in front of a token the exact reader has to look at (unary run not terminated inside
 // the view, reserved tag).  tp[0..cnt] = token starts / end, returns cnt.
-__device__ __forceinline__ uint32_t walk_tokens(const uint32_t* ring, uint32_t* tp, uint32_t wbase, uint32_t rel,
-                                                uint32_t mode, uint32_t k, uint32_t B) {
+__device__ __forceinline__ uint32_t walk_tokens(const u64* ring, uint32_t* tp, uint32_t rel, uint32_t mode,
+                                                uint32_t k, uint32_t B) {
   uint32_t cnt = 0u;
   if (mode == MODE_RICE || mode == MODE_STATIC) {
     const uint32_t k1 = k + 1u;
-    while (cnt < B) {
+#pragma unroll 4
+    for (; cnt < B; ++cnt) {
       tp[cnt] = rel;
-      const uint32_t hi = ring_peek(ring, wbase, rel);
+      const uint32_t hi = ring_peek(ring, rel);
       if (hi == 0xFFFFFFFFu) break;
       rel += (uint32_t)__clz((int)~hi) + k1;
-      ++cnt;
     }
   } else if (mode == MODE_ZR) {
-    while (cnt < B) {
+    for (; cnt < B; ++cnt) {
       tp[cnt] = rel;
-      const uint32_t hi = ring_peek(ring, wbase, rel);
+      const uint32_t hi = ring_peek(ring, rel);
       const uint32_t tag = hi >> 30;
       if (tag == 3u) break;
       if (tag == 2u) {
@@ -366,12 +373,11 @@ __device__ __forceinline__ uint32_t walk_tokens(const uint32_t* ring, uint32_t* 
         if (q >= 30u) break;
         rel += 3u + q + (tag ? kZrRunK : k);
       }
-      ++cnt;
     }
   } else {  // MODE_BIN
-    while (cnt < B) {
+    for (; cnt < B; ++cnt) {
       tp[cnt] = rel;
-      const uint32_t hi = ring_peek(ring, wbase, rel);
+      const uint32_t hi = ring_peek(ring, rel);
       const uint32_t tag = hi >> 30;
       if (tag == 0u) {
         rel += 2u;
@@ -382,7 +388,6 @@ __device__ __forceinline__ uint32_t walk_tokens(const uint32_t* ring, uint32_t* 
         if (q >= 30u) break;
         rel += 3u + q + k;
       }
-      ++cnt;
     }
   }
   tp[cnt] = rel;
@@ -411,33 +416,35 @@ __device__ __forceinline__ bool decode_segment_fast(BitRd& r, u64& pos, uint32_t
     const uint32_t left = n - idx;
     const uint32_t want = k > 26u ? 0u : (B < left ? B : left);  // k > 26: the unary limit can bind, serial reader
     stage_ensure(r, sc, stg, pos, lane);
-    const uint32_t wbase = (uint32_t)(pos >> 5), rel0 = (uint32_t)pos & 31u;
+    // ring position of `pos`, and the absolute bit position of ring position 0
+    const uint32_t rel0 = (uint32_t)pos & 4095u;
+    const u64 ring_base = pos - rel0;
     uint32_t cnt = 0u;
-    if (lane == 0u && want) cnt = walk_tokens(sc->ring, sc->tp, wbase, rel0, mode, k, want);
+    if (lane == 0u && want) cnt = walk_tokens(sc->ring, sc->tp, rel0, mode, k, want);
     cnt = __shfl_sync(kFull, cnt, 0);
     __syncwarp();
     uint32_t u = 0u, w = 0u;
     bool bad = false;
     if (lane < cnt) {
       const uint32_t s = sc->tp[lane], e = sc->tp[lane + 1u];
-      bad = (u64)wbase * 32ull + e > r.end;
+      bad = ring_base + e > r.end;
       w = 1u;
       if (mode == MODE_RICE || mode == MODE_STATIC) {
-        const uint32_t rem = k ? ring_peek(sc->ring, wbase, e - k) >> (32u - k) : 0u;
+        const uint32_t rem = k ? ring_peek(sc->ring, e - k) >> (32u - k) : 0u;
         u = ((e - s - 1u - k) << k) | rem;
       } else {
-        const uint32_t hs = ring_peek(sc->ring, wbase, s);
+        const uint32_t hs = ring_peek(sc->ring, s);
         const uint32_t tag = hs >> 30;
         if (mode == MODE_ZR && tag == 2u) {
-          u = ring_peek(sc->ring, wbase, s + 2u);
+          u = ring_peek(sc->ring, s + 2u);
         } else if (mode == MODE_ZR && tag == 1u) {
-          const uint32_t rem = ring_peek(sc->ring, wbase, e - kZrRunK) >> (32u - kZrRunK);
+          const uint32_t rem = ring_peek(sc->ring, e - kZrRunK) >> (32u - kZrRunK);
           w = (((e - s - 3u - kZrRunK) << kZrRunK) | rem) + kZrMinRun;
         } else if (mode == MODE_BIN && tag != 3u) {
           const uint32_t sign = (hs >> 29) & 1u;
           u = tag == 0u ? 0u : (tag == 1u ? (sign ? 1u : 2u) : (sign ? 3u : 4u));
         } else {  // tag 00 (zero-run mode) / 11 (bin mode): Rice(k) behind the tag
-          const uint32_t rem = k ? ring_peek(sc->ring, wbase, e - k) >> (32u - k) : 0u;
+          const uint32_t rem = k ? ring_peek(sc->ring, e - k) >> (32u - k) : 0u;
           u = ((e - s - 3u - k) << k) | rem;
         }
       }
@@ -481,7 +488,7 @@ __device__ __forceinline__ bool decode_segment_fast(BitRd& r, u64& pos, uint32_t
       const uint32_t adv = __shfl_sync(kFull, PW, (int)valid - 1);
       count += adv;
       idx += adv;
-      pos = (u64)wbase * 32ull + sc->tp[valid];
+      pos = ring_base + sc->tp[valid];
     }
     if (knew != k) {  // k moved behind token valid-1: what follows was read with the wrong k
       k = knew;
@@ -615,46 +622,81 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
   return ok != 0u;
 }
 
-// Runs step(i, value&) over x[0..n) in order, 8 samples at a time.  One thread owns the
-// whole serial recurrence, so the only thing that can hide the memory latency of the
-// in-place pattern (load x[i] -> compute -> store x[i]) is distance: the loads of chunk
-// c + D are issued when chunk c is taken out of its register slot, D = 4 chunks (32 samples,
-// ~1000 cycles of dependent arithmetic) ahead of their use.  Chunks move as 128-bit vectors
-// when the plane is 16-byte aligned (every block start of a regular stream is).
+// Asynchronous 16-byte copies global -> shared (LDGSTS) with commit groups: unlike register
+// prefetches, whose scoreboard waits also wait for the loads issued after them, a
+// wait_group leaves exactly the wanted number of newer copies in flight.
+__device__ __forceinline__ void cp_async16(int4* smem_dst, const int4* gsrc) {
+#ifdef LACB_EMU
+  *smem_dst = *gsrc;
+#else
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef LACB_EMU
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef LACB_EMU
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+constexpr int kRestoreDepth = 6;  // chunks of 8 samples in flight per thread
+
+// Runs step(i, value&) over x[0..n) in order, 8 samples at a time.  One thread owns the whole
+// serial recurrence, so memory latency of the in-place pattern (load x[i] -> compute -> store
+// x[i]) can only be hidden by distance: chunk c + kRestoreDepth is requested (cp.async into
+// the thread's own staging slots, `stage` with `stride` int4 between slots) when chunk c is
+// taken out.  Chunks move as 128-bit vectors when the plane is 16-byte aligned (every block
+// start of a regular stream is).
 template <typename Step>
-__device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, Step&& step) {
-  constexpr int D = 4;
+__device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* stage, uint32_t stride, Step&& step) {
+  constexpr int D = kRestoreDepth;
   const bool aligned = (reinterpret_cast<uint64_t>(x) & 15ull) == 0ull;
   uint32_t i = 0;
   if (aligned) {
-    int4 buf[D][2];
     const uint32_t nch = n >> 3;
     int4* x4 = reinterpret_cast<int4*>(x);
 #pragma unroll
-    for (int d = 0; d < D; ++d)
+    for (int d = 0; d < D; ++d) {
       if ((uint32_t)d < nch) {
-        buf[d][0] = x4[2 * d];
-        buf[d][1] = x4[2 * d + 1];
+        cp_async16(stage + (2 * d) * stride, x4 + 2 * d);
+        cp_async16(stage + (2 * d + 1) * stride, x4 + 2 * d + 1);
       }
+      cp_async_commit();  // one group per chunk, empty groups keep the count uniform
+    }
     for (uint32_t c0 = 0; c0 < nch; c0 += D) {
 #pragma unroll
       for (int d = 0; d < D; ++d) {
         const uint32_t c = c0 + (uint32_t)d;
         if (c < nch) {
-          int32_t v[8] = {buf[d][0].x, buf[d][0].y, buf[d][0].z, buf[d][0].w,
-                          buf[d][1].x, buf[d][1].y, buf[d][1].z, buf[d][1].w};
+          cp_async_wait<D - 1>();  // the oldest group (chunk c) has landed
+          const int4 lo = stage[(2 * d) * stride], hi = stage[(2 * d + 1) * stride];
           if (c + D < nch) {
-            buf[d][0] = x4[2 * (c + D)];
-            buf[d][1] = x4[2 * (c + D) + 1];
+            cp_async16(stage + (2 * d) * stride, x4 + 2 * (c + D));
+            cp_async16(stage + (2 * d + 1) * stride, x4 + 2 * (c + D) + 1);
           }
+          cp_async_commit();
+          int32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          // no branch per sample: the verdicts are collected and looked at once per chunk, so the
+          // scheduler can overlap the independent parts of neighbouring samples
+          bool ok = true;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (!step(c * 8u + (uint32_t)j, v[j])) return false;
+          for (int j = 0; j < 8; ++j) ok = step(c * 8u + (uint32_t)j, v[j]) && ok;
+          if (!ok) {
+            cp_async_wait<0>();
+            return false;
+          }
           x4[2 * c] = make_int4(v[0], v[1], v[2], v[3]);
           x4[2 * c + 1] = make_int4(v[4], v[5], v[6], v[7]);
         }
       }
     }
+    cp_async_wait<0>();
     i = nch << 3;
   }
   for (; i < n; ++i) {
@@ -666,37 +708,30 @@ __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, Step&& s
 }
 
 // restore_*_in_place, block/decoder.cpp:308-403: every reconstructed sample must fit int32
-__device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t type, uint32_t order, const int16_t* c) {
+__device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t type, uint32_t order, const int16_t* c,
+                                              int4* stage, uint32_t stride) {
   if (type == PRED_FIXED) {
     if (order == 0u) return true;
     i64 h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-    return restore_chunked(x, n, [&](uint32_t i, int32_t& val) {
-      i64 s = val;
-      if (i >= order) {
-        i64 p;
-        if (order == 1u) p = h1;
-        else if (order == 2u) p = 2 * h1 - h2;
-        else if (order == 3u) p = 3 * h1 - 3 * h2 + h3;
-        else p = 4 * h1 - 6 * h2 + 4 * h3 - h4;
-        s += p;
-        if (s < -2147483648ll || s > 2147483647ll) return false;
-        val = (int32_t)s;
-      }
+    return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
+      i64 p;
+      if (order == 1u) p = h1;
+      else if (order == 2u) p = 2 * h1 - h2;
+      else if (order == 3u) p = 3 * h1 - 3 * h2 + h3;
+      else p = 4 * h1 - 6 * h2 + 4 * h3 - h4;
+      const i64 s = (i64)val + (i >= order ? p : 0ll);  // the first `order` samples are verbatim
+      val = (int32_t)s;
       h4 = h3; h3 = h2; h2 = h1; h1 = s;
-      return true;
+      return s == (i64)(int32_t)s;  // a failing sample ends the block at the end of its chunk
     });
   }
   if (type == PRED_FIR) {
     i64 h1 = 0, h2 = 0;
-    return restore_chunked(x, n, [&](uint32_t i, int32_t& val) {
-      i64 s = val;
-      if (i >= 2u) {
-        s += (3 * h1 - h2) >> 2;
-        if (s < -2147483648ll || s > 2147483647ll) return false;
-        val = (int32_t)s;
-      }
+    return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
+      const i64 s = (i64)val + (i >= 2u ? ((3 * h1 - h2) >> 2) : 0ll);
+      val = (int32_t)s;
       h2 = h1; h1 = s;
-      return true;
+      return s == (i64)(int32_t)s;
     });
   }
   if (order <= 12u) {
@@ -707,19 +742,24 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
     int32_t h[13];
 #pragma unroll
     for (int t = 0; t <= 12; ++t) h[t] = 0;
-    return restore_chunked(x, n, [&](uint32_t, int32_t& val) {
+    return restore_chunked(x, n, stage, stride, [&](uint32_t, int32_t& val) {
       // taps 2..12 do not depend on the previous sample: only c1*h1 sits on the serial chain
-      i64 acc = 0;
+      // three independent partial sums: a single chain of twelve dependent multiply-adds would
+      // be longer than the recurrence's own critical path (c1 * h1 -> shift -> add -> check)
+      i64 a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
-      for (int t = 2; t <= 12; ++t) acc = mad_wide(cf[t], h[t], acc);
-      acc = mad_wide(cf[1], h[1], acc);
+      for (int t = 2; t <= 12; t += 3) {
+        a0 = mad_wide(cf[t], h[t], a0);
+        if (t + 1 <= 12) a1 = mad_wide(cf[t + 1], h[t + 1], a1);
+        if (t + 2 <= 12) a2 = mad_wide(cf[t + 2], h[t + 2], a2);
+      }
+      const i64 acc = mad_wide(cf[1], h[1], a0 + a1 + a2);
       const i64 s = (acc >> 15) + (i64)val;
-      if (s < -2147483648ll || s > 2147483647ll) return false;
       val = (int32_t)s;
 #pragma unroll
       for (int t = 12; t >= 2; --t) h[t] = h[t - 1];
       h[1] = (int32_t)s;
-      return true;
+      return s == (i64)(int32_t)s;
     });
   }
   for (uint32_t i = 0; i < n; ++i) {  // orders 13..32: legal in the format, never produced by the encoder
@@ -873,6 +913,7 @@ __global__ void __launch_bounds__(64) k_restore_blocks(DecCfg cfg, const u64* __
                                                        const ChanHdr* __restrict__ hdrs, uint32_t* blk_err,
                                                        const uint32_t* __restrict__ order,
                                                        const uint32_t* __restrict__ n_order) {
+  __shared__ int4 stage[2 * kRestoreDepth][64];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *n_order) return;
   const uint32_t j = order[i];
@@ -880,7 +921,8 @@ __global__ void __launch_bounds__(64) k_restore_blocks(DecCfg cfg, const u64* __
   const uint32_t b = j / cfg.channels, ch = j - b * cfg.channels;
   const ChanHdr* h = hdrs + (size_t)b * 2u + ch;
   int32_t* x = (ch ? R : L) + blk_fs[b];
-  if (!restore_block(x, blk_size[b], h->type, h->order, h->coef)) atomicOr(&blk_err[b], 0x100u << ch);
+  if (!restore_block(x, blk_size[b], h->type, h->order, h->coef, &stage[0][threadIdx.x], 64u))
+    atomicOr(&blk_err[b], 0x100u << ch);
 }
 // Folds the restore verdicts (bits 8/9) into the per-block code in the reference's order:
 // primary parse, primary reconstruction, secondary parse, secondary reconstruction.

@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(NT) k_autocorr(PcmSrc src, const uint32_t* job
     const uint32_t slot = jobs[ji];
     JobDesc jd;
     job_desc<PROBE>(src, slot, jd);
-    for (uint32_t i = tid; i < (uint32_t)(NT * E); i += NT) X[swz(i)] = i < jd.n ? load_sample(src, jd.kind, jd.start + i) : 0;
+    {
+      ASmem<NT, E> xs{smraw};  // only the X plane of the layout is used (and allocated) here
+      load_block<NT, E>(xs, src, jd.kind, jd.start, jd.n);
+    }
     if (tid < 13u) red[tid] = 0ull;
     __syncthreads();
     int32_t x[E + 12];
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(NT) k_autocorr(PcmSrc src, const uint32_t* job
     for (int j = 0; j < E; ++j) {
       // samples past n and before 0 are zero in X, so every term outside the sums vanishes
 #pragma unroll
-      for (int k = 0; k < 13; ++k) s[k] += (u64)((i64)x[12 + j] * (i64)x[12 + j - k]);
+      for (int k = 0; k < 13; ++k) s[k] = (u64)mad_wide(x[12 + j], x[12 + j - k], (i64)s[k]);
     }
 #pragma unroll
     for (int k = 0; k < 13; ++k) {

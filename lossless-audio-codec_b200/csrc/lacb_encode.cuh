@@ -117,11 +117,61 @@ struct ASmem {
 
 // ---------------------------------------------------------------------------
 // load the channel-block into the swizzled X plane (zero padded to CAP)
+__device__ __forceinline__ int32_t combine_sample(int kind, int32_t l, int32_t r) {
+  if (kind == 0) return l;
+  if (kind == 1) return r;
+  if (kind == 2) return (int32_t)((uint32_t)l + (uint32_t)r) >> 1;
+  return (int32_t)((uint32_t)l - (uint32_t)r);
+}
+
+// Loads the channel-block into the swizzled X plane (zero padded to CAP) and returns the OR of
+// the sample magnitudes this thread saw.  All of a thread's 128-bit loads are issued before the
+// first one is consumed: with one resident CTA per SM nothing else hides the HBM latency.
 template <int NT, int E>
 __device__ __forceinline__ uint32_t load_block(const ASmem<NT, E>& sm, const PcmSrc& src, int kind, u64 start,
                                                uint32_t n) {
   int32_t* X = sm.X();
   uint32_t mag = 0u;  // OR of the magnitudes (v >= 0 ? v : ~v) of the samples this thread loaded
+  constexpr int Q = E / 4;  // 16-byte chunks per thread
+  const bool vec_ok = ((reinterpret_cast<uint64_t>(src.L + start) & 15ull) == 0ull) &&
+                      (kind == 0 || (reinterpret_cast<uint64_t>(src.R + start) & 15ull) == 0ull);
+  if (vec_ok) {
+    const int4* L4 = reinterpret_cast<const int4*>(src.L + start);
+    const int4* R4 = reinterpret_cast<const int4*>((kind ? src.R : src.L) + start);
+    int4 a[Q], b[Q];
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const uint32_t q = (uint32_t)k * NT + threadIdx.x;
+      a[k] = make_int4(0, 0, 0, 0);
+      b[k] = make_int4(0, 0, 0, 0);
+      if (q * 4u + 4u <= n) {
+        if (kind != 1) a[k] = L4[q];
+        if (kind != 0) b[k] = R4[q];
+      } else if (q * 4u < n) {  // the chunk straddling the end of the block
+        int32_t t[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
+        for (uint32_t m = 0; m < 4u; ++m)
+          if (q * 4u + m < n) {
+            if (kind != 1) t[m] = src.L[start + q * 4u + m];
+            if (kind != 0) w[m] = src.R[start + q * 4u + m];
+          }
+        a[k] = make_int4(t[0], t[1], t[2], t[3]);
+        b[k] = make_int4(w[0], w[1], w[2], w[3]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < Q; ++k) {
+      const uint32_t q = (uint32_t)k * NT + threadIdx.x;
+      int4 v;
+      v.x = combine_sample(kind, a[k].x, b[k].x);
+      v.y = combine_sample(kind, a[k].y, b[k].y);
+      v.z = combine_sample(kind, a[k].z, b[k].z);
+      v.w = combine_sample(kind, a[k].w, b[k].w);
+      mag |= (uint32_t)(v.x ^ (v.x >> 31)) | (uint32_t)(v.y ^ (v.y >> 31)) | (uint32_t)(v.z ^ (v.z >> 31)) |
+             (uint32_t)(v.w ^ (v.w >> 31));
+      reinterpret_cast<int4*>(X)[swz_chunk(q)] = v;
+    }
+    return mag;
+  }
   for (uint32_t i = threadIdx.x; i < ASmem<NT, E>::CAP; i += NT) {
     int32_t v = 0;
     if (i < n) v = load_sample(src, kind, start + i);
@@ -566,8 +616,8 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
         const u64 lm_max = (W0 + S_own + 128ull) >> 8, lm_min = (W0 - S_leave + 128ull) >> 8;
         const u64 N_lo = pr.Pex + (c_first >> 1), N_hi = pr.Pex + S_own + (c_last >> 1);
         const u64 tA_max = (3ull * lm_max + 3ull) >> 2, tB_min = lm_min + 2ull + lm_min / 3ull;
-        if (N_lo >= tA_max * c_last && N_hi < tB_min * c_first) {
-          drift = 0;
+        if ((N_lo >= tA_max * c_last && N_hi < tB_min * c_first) || N_hi < (u64)c_first) {
+          drift = 0;  // inside the dead band everywhere, or the running mean is 0 (rule off) everywhere
         } else {
           const u64 tA_min = (3ull * lm_min + 3ull) >> 2, tB_max = lm_max + 2ull + lm_max / 3ull;
           if (N_hi < tA_min * c_first && N_lo >= (u64)c_last) drift = 1;
@@ -881,7 +931,31 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
       plain = false;
     }
   }
-  if (!plain)
+  // Silent chunks -- all E samples and the four after them zero, no segment boundary within
+  // reach: every sample sits inside a zero run that closes later (zero-run cost 0, no run
+  // closed here), takes 2 bits as a bin code and 1 + k as a Rice code.
+  bool silent = false;
+  if (!plain && sg.fast && pr.any4 && (pr.zmask & ((1u << E) - 1u)) == ((1u << E) - 1u) &&
+      (sg.bnd == 0xFFFFFFFFu || sg.bnd >= g0 + (uint32_t)E + 4u)) {
+    const uint32_t zm = zero_lookahead(sm, pr, n);
+    if ((zm >> E) == 0xFu) {
+      const uint32_t* K = sm.Kpl() + tid * (E / 4);
+      uint32_t kprev = tid ? (K[-1] >> 24) : 0u;
+      if (g0 == sg.a0) kprev = kinitA;
+      uint32_t ksum = kprev;
+#pragma unroll
+      for (int c4 = 0; c4 < E / 4; ++c4) {
+        const uint32_t kw = K[c4];
+        ksum += (kw & 0xFFu) + ((kw >> 8) & 0xFFu) + ((kw >> 16) & 0xFFu) + ((kw >> 24) & 0xFFu);
+      }
+      ksum -= K[E / 4 - 1] >> 24;  // the last k belongs to the next chunk's first sample
+      riceA = (u64)(ksum + (uint32_t)E);
+      binA = 2ull * (uint32_t)E;
+      zrA = 0ull;
+      silent = true;
+    }
+  }
+  if (!plain && !silent)
   walk_items<NT, E>(sm, pr, n, sg, kinitA, kinitB,
                     [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
                         bool long_run) {

@@ -1,3 +1,3 @@
 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -2 gpurun_out/pytest_gpu.log
-python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1r.json 2>gpurun_out/bench_r1r.err; python -c "
-import json;d=json.load(open('gpurun_out/bench_r1r.json'));print('value',round(d['value'],2),'e2e',round(d['e2e']['value'],2),d['stage_ms_per_step'])"
+python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1v.json 2>gpurun_out/bench_r1v.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_r1v.json'));print('value',round(d['value'],2),'e2e',round(d['e2e']['value'],2),d['stage_ms_per_step'])"
