@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--seconds", type=int, default=600, help="audio seconds per GPU (configs[1] = 600)")
     ap.add_argument("--cpu-seconds", type=int, default=60, help="audio seconds of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-contexts", type=int, default=4, help="contexts (host threads) the e2e leg splits the blocks over")
+    ap.add_argument("--e2e-contexts", type=int, default=1, help="contexts (host threads) the e2e leg splits the blocks over")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -326,6 +326,15 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        # DRAM bytes of one k_analyze launch from the committed `ncu --set full` capture of this same
+        # command (profiles/r1_roofline_traffic.json, written by tools/ncu_traffic.py); null without it
+        traffic = None
+        try:
+            tj = json.loads((ROOT / "profiles" / "r1_roofline_traffic.json").read_text())
+            if tj.get("frames_per_gpu") == frames:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         analyze_s = stats["analyze_ms"] / K / 1e3
         parse_s = stats["parse_ms"] / K / 1e3
         achieved = (pcm_bytes + lac) / analyze_s / 1e9
@@ -342,7 +351,7 @@ def main():
             "stage_ms_per_step": {k: round(v / K, 4) for k, v in sorted(stats["stages"].items())},
             "roofline": {"bound": "hbm", "kernel": "k_analyze<1024,16> (encoder channel-block search)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None,
+                         "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_launch": pcm_bytes + lac},
             "roofline_decode": {"bound": "hbm", "kernel": "k_parse_blocks (serial bitstream parse, one warp per block)",
@@ -351,7 +360,10 @@ def main():
             "e2e": {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": pcm_bytes + lac_e2e, "d2h_bytes_per_step": lac_e2e + pcm_bytes,
                     "steps": e2e_steps, "contexts": nctx},
-            "gpu_launches": K * 10,
+            # per step: k_deinterleave, k_plan_fixed, k_build_jobs, k_autocorr, k_levinson, k_analyze,
+            # k_finalize_blocks, k_emit (encode) + k_parse_blocks, k_restore_order, k_restore_blocks,
+            # k_merge_restore_errors, k_finish_pcm (decode)
+            "gpu_launches": K * 13,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:

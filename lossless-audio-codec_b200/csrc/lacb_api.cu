@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -40,6 +41,9 @@ struct lacb_ctx {
   DevBuf d_payload, d_fs, d_size, d_boff, d_bytes, d_err, d_ms, d_L, d_R, d_packed, d_hdrs, d_order;
   void* pinned = nullptr;
   size_t pinned_cap = 0;
+  uint32_t* hmisc = nullptr;        // pinned: range error, size error, total bytes (2 words)
+  cudaEvent_t ev_misc = nullptr;    // hmisc has landed
+  std::vector<lacb_ctx*> kids;      // slice contexts of the pipelined host paths (own stream + workspace)
   lacb_block_info last_info{};
 };
 
@@ -101,10 +105,11 @@ T* as(DevBuf& b) {
 }
 uint32_t lacb_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
-// Device part of the encoder: planes already on the device.  On success the payload is
-// in ctx->payload, the per-block sizes in ctx->blk_bytes, *total the payload size.
-int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL, const int32_t* dR,
-                     uint64_t frames, bool validate, uint64_t* total, lacb_err* err) {
+// First half of the device encoder (planes already on the device): everything up to the
+// per-block sizes and payload offsets, whose totals are copied to pinned host memory
+// asynchronously.  Nothing here waits for the device.
+int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL, const int32_t* dR,
+                    uint64_t frames, bool validate) {
   cudaStream_t st = ctx->stream;
   const uint64_t nb64 = (frames + kMaxBlock - 1) / kMaxBlock;
   const uint32_t nb = (uint32_t)nb64;
@@ -194,9 +199,30 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
                 as<uint32_t>(ctx->blk_bytes), as<u64>(ctx->blk_off), reinterpret_cast<u64*>(miscw + 2), miscw + 1);
   }
   CK(cudaEventRecord(ctx->ev[EV_FINAL], st));
-  uint32_t hmisc[4];
-  CK(cudaMemcpyAsync(hmisc, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (!ctx->hmisc) {
+    CK(cudaMallocHost(reinterpret_cast<void**>(&ctx->hmisc), 64));
+    CK(cudaEventCreateWithFlags(&ctx->ev_misc, cudaEventDisableTiming));
+  }
+  CK(cudaMemcpyAsync(ctx->hmisc, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev_misc, st));
+  return 0;
+}
+
+// Second half of the device encoder: waits for the sizes of encode_analysis, sizes the payload
+// buffer and launches the emitter.
+int encode_emit(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL, const int32_t* dR, uint64_t frames,
+                uint64_t* total, lacb_err* err) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
+  EncCfg cfg;
+  cfg.channels = prm->channels;
+  cfg.stereo_mode = prm->channels == 2 ? prm->stereo_mode : 0u;
+  cfg.zero_run = prm->zero_run_enabled;
+  cfg.partitioning = prm->partitioning_enabled;
+  cfg.n_blocks = nb;
+  PcmSrc src{dL, prm->channels == 2 ? dR : nullptr, frames};
+  const uint32_t* hmisc = ctx->hmisc;
+  CK(cudaEventSynchronize(ctx->ev_misc));
   CK(cudaGetLastError());
   if (hmisc[0]) {
     ctx->err = "sample outside bit depth range";
@@ -219,6 +245,14 @@ int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* d
   }
   CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
   return 0;
+}
+
+// Device part of the encoder: planes already on the device.  On success the payload is
+// in ctx->payload, the per-block sizes in ctx->blk_bytes, *total the payload size.
+int encode_on_device(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL, const int32_t* dR,
+                     uint64_t frames, bool validate, uint64_t* total, lacb_err* err) {
+  CKR(encode_analysis(ctx, prm, dL, dR, frames, validate));
+  return encode_emit(ctx, prm, dL, dR, frames, total, err);
 }
 
 void fill_enc_timing(lacb_ctx* ctx) {
@@ -308,6 +342,9 @@ void lacb_destroy(lacb_ctx* ctx) {
                    &ctx->d_size, &ctx->d_boff, &ctx->d_bytes, &ctx->d_err, &ctx->d_ms, &ctx->d_L, &ctx->d_R,
                    &ctx->d_packed, &ctx->d_hdrs, &ctx->d_order};
   for (DevBuf* b : all) release(*b);
+  for (lacb_ctx* k : ctx->kids) lacb_destroy(k);
+  if (ctx->hmisc) cudaFreeHost(ctx->hmisc);
+  if (ctx->ev_misc) cudaEventDestroy(ctx->ev_misc);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < EV_COUNT; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -421,6 +458,184 @@ int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Pipelined host paths.  A long input is cut into slices of whole blocks; two slice contexts
+// (own stream, own workspace) alternate, so the host->device copy of slice i+1 and the
+// device->host copy of slice i-1 run under the kernels of slice i.  Blocks are independent, so
+// the bytes are those of a single pass.  A slice holds a multiple of the SM count of
+// channel-block jobs: the persistent analysis grid then ends on a full wave.
+static uint32_t slice_blocks(const lacb_ctx* ctx, uint32_t channels) {
+  static const long forced = getenv("LACB_SLICE_BLOCKS") ? atol(getenv("LACB_SLICE_BLOCKS")) : 0;  // tests / tuning
+  if (forced > 0) return (uint32_t)forced;
+  const uint32_t per_wave = ((uint32_t)ctx->sms + channels - 1u) / channels;  // blocks per wave of jobs
+  return per_wave * 14u;
+}
+static double trace_now() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static bool trace_on() {
+  static const bool on = getenv("LACB_TRACE") != nullptr;
+  return on;
+}
+#define TRACE(...)                                   \
+  do {                                               \
+    if (trace_on()) {                                \
+      fprintf(stderr, "[lacb %.3f] ", trace_now());  \
+      fprintf(stderr, __VA_ARGS__);                  \
+      fprintf(stderr, "\n");                         \
+    }                                                \
+  } while (0)
+static int ensure_kids(lacb_ctx* ctx) {
+  while (ctx->kids.size() < 2) {
+    lacb_ctx* k = nullptr;
+    const int rc = lacb_create(ctx->device, &k);
+    if (rc != 0) {
+      ctx->err = "cannot create slice context";
+      return rc;
+    }
+    ctx->kids.push_back(k);
+  }
+  return 0;
+}
+#define CKK(kid, expr)                \
+  do {                                \
+    const int _r = (expr);            \
+    if (_r != 0) {                    \
+      ctx->err = (kid)->err;          \
+      cudaDeviceSynchronize();        \
+      return _r;                      \
+    }                                 \
+  } while (0)
+
+// host -> device copy of one slice plus the first half of its encode, nothing waits
+static int enc_slice_begin(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a,
+                           const void* pcm_b, uint64_t f0, uint64_t fr) {
+  cudaStream_t st = ctx->stream;
+  CKR(ensure(ctx, ctx->planeL, fr * 4));
+  if (prm->channels == 2) CKR(ensure(ctx, ctx->planeR, fr * 4));
+  bool validate = prm->validate_range != 0;
+  if (layout == LACB_PLANAR_I32) {
+    CK(cudaMemcpyAsync(ctx->planeL.p, static_cast<const int32_t*>(pcm_a) + f0, fr * 4, cudaMemcpyHostToDevice, st));
+    if (prm->channels == 2)
+      CK(cudaMemcpyAsync(ctx->planeR.p, static_cast<const int32_t*>(pcm_b) + f0, fr * 4, cudaMemcpyHostToDevice, st));
+  } else {
+    const uint32_t bps = prm->bit_depth / 8;
+    const size_t fb = (size_t)prm->channels * bps;
+    CKR(ensure(ctx, ctx->packed_in, fr * fb + 4));
+    CK(cudaMemcpyAsync(ctx->packed_in.p, static_cast<const uint8_t*>(pcm_a) + f0 * fb, fr * fb, cudaMemcpyHostToDevice,
+                       st));
+    const uint32_t grid = lacb_umin((uint32_t)((fr + 255) / 256), (uint32_t)ctx->sms * 16u);
+    auto kd = k_deinterleave;
+    LACB_LAUNCH(kd, grid ? grid : 1u, 256, 0, st, as<uint8_t>(ctx->packed_in), (u64)fr, prm->channels, bps,
+                as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR));
+    validate = false;
+  }
+  return encode_analysis(ctx, prm, as<int32_t>(ctx->planeL), as<int32_t>(ctx->planeR), fr, validate);
+}
+
+static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a,
+                              const void* pcm_b, uint64_t frames, uint8_t* dst, uint64_t dst_cap,
+                              uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes, lacb_err* err) {
+  CKR(ensure_kids(ctx));
+  const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
+  const uint32_t sb = slice_blocks(ctx, prm->channels);
+  const uint32_t ns = (nb + sb - 1u) / sb;
+  uint8_t* host = dst;
+  uint64_t cap = dst_cap;
+  if (!dst) {  // library-owned result: start from the raw size, grow if a stream expands
+    cap = frames * prm->channels * (prm->bit_depth / 8) + (uint64_t)nb * 8 + 4096;
+    host = (uint8_t*)malloc(cap);
+    if (!host) return LACB_ENOMEM;
+  }
+  auto slice_range = [&](uint32_t i, uint64_t* f0, uint64_t* fr) {
+    const uint64_t b0 = (uint64_t)i * sb, b1 = b0 + sb < nb ? b0 + sb : nb;
+    *f0 = b0 * kMaxBlock;
+    const uint64_t f1 = b1 * kMaxBlock < frames ? b1 * kMaxBlock : frames;
+    *fr = f1 - *f0;
+  };
+  auto fail = [&](int rc) {
+    cudaDeviceSynchronize();
+    if (!dst) free(host);
+    return rc;
+  };
+  uint64_t f0, fr;
+  slice_range(0, &f0, &fr);
+  {
+    const int rc = enc_slice_begin(ctx->kids[0], prm, layout, pcm_a, pcm_b, f0, fr);
+    if (rc != 0) { ctx->err = ctx->kids[0]->err; return fail(rc); }
+  }
+  uint64_t off = 0;
+  bool overflow = false;
+  // per-block sizes land in page-locked memory first: a device->host copy into the caller's
+  // pageable array would block the host at every slice and serialise the pipeline
+  uint32_t* bb_stage = nullptr;
+  if (block_bytes) {
+    const int rc = ensure_pinned(ctx, (size_t)nb * 4);
+    if (rc != 0) return fail(rc);
+    bb_stage = static_cast<uint32_t*>(ctx->pinned);
+  }
+  for (uint32_t i = 0; i < ns; ++i) {
+    lacb_ctx* k = ctx->kids[i & 1u];
+    if (i + 1u < ns) {  // next slice: copies and analysis queue up behind slice i - 1 on the other stream
+      uint64_t g0, gr;
+      slice_range(i + 1u, &g0, &gr);
+      lacb_ctx* kn = ctx->kids[(i + 1u) & 1u];
+      const int rc = enc_slice_begin(kn, prm, layout, pcm_a, pcm_b, g0, gr);
+      if (rc != 0) { ctx->err = kn->err; return fail(rc); }
+      TRACE("enc slice %u queued", i + 1u);
+    }
+    slice_range(i, &f0, &fr);
+    uint64_t total = 0;
+    const int rc = encode_emit(k, prm, as<int32_t>(k->planeL), as<int32_t>(k->planeR), fr, &total, err);
+    if (rc != 0) { ctx->err = k->err; return fail(rc); }
+    TRACE("enc slice %u sizes known, emit queued (%llu bytes)", i, (unsigned long long)total);
+    const uint32_t nbs = (uint32_t)((fr + kMaxBlock - 1) / kMaxBlock);
+    if (off + total > cap) {
+      if (dst) {
+        overflow = true;  // keep going without copying: the caller is told the size it needs
+      } else {
+        cudaDeviceSynchronize();  // copies into the old buffer must have landed
+        cap = (off + total) * 2;
+        uint8_t* bigger = (uint8_t*)realloc(host, cap);
+        if (!bigger) return fail(LACB_ENOMEM);
+        host = bigger;
+      }
+    }
+    if (!overflow)
+      CKK(k, [&]() -> int {
+        lacb_ctx* ctx = k;  // CK reports into the slice context
+        CK(cudaMemcpyAsync(host + off, ctx->payload.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+        return 0;
+      }());
+    if (bb_stage)
+      CKK(k, [&]() -> int {
+        lacb_ctx* ctx = k;
+        CK(cudaMemcpyAsync(bb_stage + (size_t)i * sb, ctx->blk_bytes.p, (size_t)nbs * 4, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        return 0;
+      }());
+    off += total;
+  }
+  for (lacb_ctx* k : ctx->kids) {
+    if (cudaStreamSynchronize(k->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      ctx->err = "CUDA failure in the sliced encoder";
+      return fail(LACB_ECUDA);
+    }
+  }
+  TRACE("enc drained");
+  memset(&ctx->timing, 0, sizeof ctx->timing);  // stage times are per slice context, not aggregated
+  if (block_bytes) memcpy(block_bytes, bb_stage, (size_t)nb * 4);
+  *payload_bytes = off;
+  if (overflow) {
+    ctx->err = "payload buffer too small";
+    return LACB_ENOMEM;
+  }
+  if (payload_out) *payload_out = host;
+  return 0;
+}
+
 static int encode_host(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,
                        uint64_t frames, uint8_t* dst, uint64_t dst_cap, uint8_t** payload_out,
                        uint64_t* payload_bytes, uint32_t* block_bytes, lacb_err* err) {
@@ -437,6 +652,9 @@ static int encode_host(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, co
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
+  if (nb >= 2u * slice_blocks(ctx, prm->channels))
+    return encode_host_sliced(ctx, prm, layout, pcm_a, pcm_b, frames, dst, dst_cap, payload_out, payload_bytes,
+                              block_bytes, err);
   CKR(ensure(ctx, ctx->planeL, frames * 4));
   if (prm->channels == 2) CKR(ensure(ctx, ctx->planeR, frames * 4));
   CK(cudaEventRecord(ctx->ev[EV_START], st));
@@ -640,7 +858,8 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   return 0;
 }
 
-static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err, bool serial = false) {
+static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err, bool serial = false,
+                               uint32_t base_block = 0) {
   std::vector<uint32_t> herr(n_blocks);
   uint32_t info[2] = {n_blocks, 0u};
   CK(cudaMemcpyAsync(herr.data(), ctx->d_err.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -655,13 +874,17 @@ static int decode_check_errors(lacb_ctx* ctx, uint32_t n_blocks, lacb_err* err, 
     char msg[160];
     switch (herr[b]) {
       case DERR_FLAG: snprintf(msg, sizeof msg, "[decode-error] invalid per-block stereo flag"); break;
-      case DERR_PRIMARY: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=primary", b); break;
-      case DERR_SECONDARY: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=secondary", b); break;
+      case DERR_PRIMARY: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=primary", base_block + b); break;
+      case DERR_SECONDARY:
+        snprintf(msg, sizeof msg, "[decode-error] block=%u channel=secondary", base_block + b);
+        break;
       case DERR_RANGE: snprintf(msg, sizeof msg, "[decode-error] decoded sample outside PCM bit depth"); break;
-      default: snprintf(msg, sizeof msg, "[decode-error] block=%u channel=trailing-payload", b); break;
+      default:
+        snprintf(msg, sizeof msg, "[decode-error] block=%u channel=trailing-payload", base_block + b);
+        break;
     }
     ctx->err = msg;
-    set_err(err, LACB_EDECODE, b, herr[b], msg);
+    set_err(err, LACB_EDECODE, base_block + b, herr[b], msg);
     return LACB_EDECODE;
   }
   if (serial && info[1]) {
@@ -737,6 +960,76 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
     frames += block_sizes[b];
   }
   const uint32_t bps = prm->bit_depth / 8;
+  // The parser (one warp per block) and the restore kernel (one thread per channel-block) are serial
+  // chains: below ~32 blocks per SM a launch takes as long as a single block, so cutting a decode
+  // into slices only pays for very long inputs (measured: 3516 blocks decode faster in one piece).
+  const uint32_t dec_sb = getenv("LACB_SLICE_BLOCKS") ? slice_blocks(ctx, prm->channels) : (uint32_t)ctx->sms * 32u;
+  if (block_bytes && n_blocks >= 2u * dec_sb) {
+    // pipelined: slices of whole blocks alternate between two slice contexts (see encode_host_sliced)
+    CKR(ensure_kids(ctx));
+    const uint32_t sb = dec_sb;
+    const uint32_t ns = (n_blocks + sb - 1u) / sb;
+    u64 tot_bytes = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) tot_bytes += block_bytes[b];
+    if (tot_bytes > payload_bytes) {
+      ctx->err = "compressed block sizes exceed frame payload";
+      set_err(err, LACB_EDECODE, 0, 0, "[decode-error] compressed block sizes exceed frame payload");
+      return LACB_EDECODE;
+    }
+    u64 boff = 0, foff = 0;
+    u64 s_b0[2] = {0, 0};
+    auto begin = [&](uint32_t i) -> int {
+      lacb_ctx* k = ctx->kids[i & 1u];
+      const uint32_t b0 = i * sb, b1 = b0 + sb < n_blocks ? b0 + sb : n_blocks;
+      u64 sbytes = 0, sframes = 0;
+      for (uint32_t b = b0; b < b1; ++b) {
+        sbytes += block_bytes[b];
+        sframes += block_sizes[b];
+      }
+      lacb_ctx* ctx = k;  // CK / CKR report into the slice context
+      CKR(ensure(ctx, ctx->d_payload, sbytes + 64));
+      CKR(ensure(ctx, ctx->d_L, sframes * 4));
+      if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, sframes * 4));
+      if (layout == LACB_PACKED_LE) CKR(ensure(ctx, ctx->d_packed, sframes * prm->channels * bps));
+      CK(cudaMemcpyAsync(ctx->d_payload.p, payload + boff, sbytes, cudaMemcpyHostToDevice, ctx->stream));
+      CKR(decode_common(ctx, prm, as<uint8_t>(ctx->d_payload), sbytes, block_sizes + b0, block_bytes + b0, b1 - b0,
+                        as<int32_t>(ctx->d_L), as<int32_t>(ctx->d_R),
+                        layout == LACB_PACKED_LE ? as<uint8_t>(ctx->d_packed) : nullptr, err));
+      if (layout == LACB_PACKED_LE) {
+        CK(cudaMemcpyAsync(static_cast<uint8_t*>(out_a) + foff * prm->channels * bps, ctx->d_packed.p,
+                           sframes * prm->channels * bps, cudaMemcpyDeviceToHost, ctx->stream));
+      } else {
+        CK(cudaMemcpyAsync(static_cast<int32_t*>(out_a) + foff, ctx->d_L.p, sframes * 4, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+        if (prm->channels == 2)
+          CK(cudaMemcpyAsync(static_cast<int32_t*>(out_b) + foff, ctx->d_R.p, sframes * 4, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+      }
+      s_b0[i & 1u] = b0;
+      boff += sbytes;
+      foff += sframes;
+      return 0;
+    };
+    int rc = begin(0);
+    for (uint32_t i = 0; i < ns && rc == 0; ++i) {
+      if (i + 1u < ns) rc = begin(i + 1u);
+      if (rc != 0) {
+        ctx->err = ctx->kids[(i + 1u) & 1u]->err;
+        break;
+      }
+      lacb_ctx* k = ctx->kids[i & 1u];
+      const uint32_t b0 = i * sb, b1 = b0 + sb < n_blocks ? b0 + sb : n_blocks;
+      TRACE("dec slice %u queued, waiting for slice %u", i + 1u, i);
+      rc = decode_check_errors(k, b1 - b0, err, false, b0);  // waits for slice i only
+      TRACE("dec slice %u done", i);
+      if (rc != 0) ctx->err = k->err;
+    }
+    if (rc != 0 && ctx->err.empty()) ctx->err = ctx->kids[0]->err;
+    cudaDeviceSynchronize();
+    (void)s_b0;
+    memset(&ctx->timing, 0, sizeof ctx->timing);
+    return rc;
+  }
   CKR(ensure(ctx, ctx->d_payload, payload_bytes + 64));
   CKR(ensure(ctx, ctx->d_L, frames * 4));
   if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, frames * 4));

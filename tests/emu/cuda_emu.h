@@ -332,7 +332,7 @@ typedef void* cudaStream_t;
 typedef struct emu_event { double t; }* cudaEvent_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaEventDefault = 0 };
+enum { cudaHostAllocDefault = 0, cudaStreamNonBlocking = 1, cudaEventDefault = 0, cudaEventDisableTiming = 2 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { int multiProcessorCount; char name[64]; size_t totalGlobalMem; int major, minor; };
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : 2; }
@@ -366,6 +366,7 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
 }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new emu_event{0}; return 0; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new emu_event{0}; return 0; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return 0; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }

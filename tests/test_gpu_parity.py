@@ -233,3 +233,47 @@ def test_serial_v2_streams(cd, name):
             assert ea == eg
             if a is not None:
                 assert np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1])
+
+
+SLICED_SCRIPT = """
+import sys
+sys.path.insert(0, {tests!r})
+import numpy as np, helpers as H
+cd = H.{codec}()
+for depth, mode, ch in ((16, 2, 2), (24, 1, 2), (24, 0, 1)):
+    l, r = H.synth(7, 7 * 16384 + 999, depth, ch)
+    want = H.oracle().encode(l, r if ch == 2 else None, 48000, depth, mode)
+    got = cd.encode(l, r if ch == 2 else None, 48000, depth, mode)
+    assert got == want, (depth, mode, ch, len(got), len(want))
+    dl, dr, hdr = cd.decode(want)
+    assert np.array_equal(dl, l) and (ch == 1 or np.array_equal(dr, r))
+    bad = bytearray(want); bad[len(bad) * 3 // 4] ^= 0x40
+    try:
+        a, ea = H.oracle().decode(bytes(bad)), None
+    except RuntimeError as e:
+        a, ea = None, str(e)
+    try:
+        g, eg = cd.decode(bytes(bad)), None
+    except RuntimeError as e:
+        g, eg = None, str(e)
+    assert ea == eg, (ea, eg)
+print("sliced ok")
+"""
+
+
+def run_sliced(codec: str, slice_blocks: int):
+    """The pipelined host paths (slices of whole blocks alternating between two slice contexts)
+    must give the bytes / samples / verdicts of a single pass; LACB_SLICE_BLOCKS forces small
+    slices so that an 8-block input is cut into several."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, LACB_SLICE_BLOCKS=str(slice_blocks))
+    out = subprocess.run([sys.executable, "-c", SLICED_SCRIPT.format(tests=str(H.ROOT / "tests"), codec=codec)],
+                         env=env, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0 and "sliced ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("slice_blocks", [1, 3])
+def test_sliced_host_pipeline(slice_blocks):
+    run_sliced("gpu_codec", slice_blocks)
