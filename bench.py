@@ -143,7 +143,7 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64", "data": "synthetic",
-        "config": workload_config(args, secs),
+        "config": workload_config(args, args.seconds),  # the GPU arm's workload; each step times `sample` of it
         "encode_gbs": pk.size * args.steps / te / 1e9, "decode_gbs": pk.size * args.steps / td / 1e9,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
