@@ -358,9 +358,9 @@ void lacb_free(void* p) { free(p); }
 // debug builds only (tools/phase_clk.py): copies out and optionally clears the phase clock table
 int lacb_debug_phase_clk(unsigned long long* out64, int reset) {
   cudaDeviceSynchronize();
-  if (out64 && cudaMemcpyFromSymbol(out64, lacb::g_phase_clk, 64 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (out64 && cudaMemcpyFromSymbol(out64, lacb::g_phase_clk, 160 * sizeof(unsigned long long)) != cudaSuccess) return -1;
   if (reset) {
-    unsigned long long z[64] = {0};
+    unsigned long long z[160] = {0};
     cudaMemcpyToSymbol(lacb::g_phase_clk, z, sizeof z);
   }
   return 0;

@@ -40,7 +40,7 @@ typedef long long i64;
 // Optional phase clocks (-DLACB_PHASE_CLK, tools/phase_clk.py): cycles every warp spends in
 // each numbered phase of k_analyze, accumulated in a global table.  Compiled out of the product.
 #if defined(LACB_PHASE_CLK) && !defined(LACB_EMU)
-__device__ unsigned long long g_phase_clk[64];
+__device__ unsigned long long g_phase_clk[64 + 3 * 32];  // [64 + 32 * i + warp]: busy cycles of phases 6 / 8 / 10 per warp
 struct PhState { long long last[32]; int base; };
 __device__ __forceinline__ PhState* ph_state() { __shared__ PhState st; return &st; }
 __device__ __forceinline__ void ph_init(int base) {
@@ -54,6 +54,8 @@ __device__ __forceinline__ void ph_mark(int id) {
   if ((threadIdx.x & 31u) == 0u && st->base >= 0) {
     const long long t = clock64();
     atomicAdd(&g_phase_clk[st->base + id], (unsigned long long)(t - st->last[threadIdx.x >> 5]));
+    if (st->base == 0 && (id == 6 || id == 8 || id == 10))
+      atomicAdd(&g_phase_clk[64 + 32 * ((id - 6) >> 1) + (threadIdx.x >> 5)], (unsigned long long)(t - st->last[threadIdx.x >> 5]));
     st->last[threadIdx.x >> 5] = t;
   }
 }

@@ -411,13 +411,23 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
         continue;
       }
 #endif
-      // initial / static k of the whole block: every warp evaluates them on its own (one k per
-      // lane) from the block totals, so no thread waits on a serial search
-      u64 stat;
-      const uint32_t k_init = warp_best_static_k(mi->p_first, mi->cnt_first, n < 256u ? n : 256u, 12, nullptr);
-      const uint32_t k_stat = warp_best_static_k(mi->u_total, mi->cnt_tot, n, 15, &stat);
-      const uint32_t has_run = cost_pass<NT, E, true>(sm, pr, n, 0u, k_init);
+      // initial / static k of the whole block from the block totals, one k per lane.  Only thread 0
+      // consumes them (two barriers later), so the last warp -- on average the least loaded one, the
+      // first warps carry the block start where k moves most -- evaluates them for everybody.
+      if ((tid >> 5) == (uint32_t)(NT / 32 - 1)) {
+        u64 sb;
+        const uint32_t ki = warp_best_static_k(mi->p_first, mi->cnt_first, n < 256u ? n : 256u, 12, nullptr);
+        const uint32_t ks = warp_best_static_k(mi->u_total, mi->cnt_tot, n, 15, &sb);
+        if ((tid & 31u) == 0u) {
+          mi->k_init = ki;
+          mi->k_stat = ks;
+          mi->stat_bits = sb;
+        }
+      }
+      const uint32_t has_run = cost_pass<NT, E, true>(sm, pr, n, 0u, 0u);
       if (tid == 0u) {
+        const u64 stat = mi->stat_bits;
+        const uint32_t k_init = mi->k_init, k_stat = mi->k_stat;
         const u64 rice = mi->tot_rice, bin = mi->tot_bin;
         const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
         const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
@@ -497,13 +507,15 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
 
     // partition search, block/encoder.cpp:486-545
     for (uint32_t p = 1u; p <= max_p; ++p) {
-      cost_pass<NT, E, false>(sm, pr, n, p, 0u);
+      const bool sums = cost_pass<NT, E, false>(sm, pr, n, p, 0u) != 0u;  // Fb: per-segment sums or prefixes
       const uint32_t cnt = 1u << p;
       const u64* Fb = sm.Fb();
-      u64 part_sum = 0ull;
+      u64* SelBits = sm.SelBits();
       for (uint32_t s = tid; s < cnt; s += NT) {
         const uint32_t sid = cnt - 1u + s;
-        const u64 rice = Fb[s + 1u] - Fb[s], zr = Fb[258 + s + 1u] - Fb[258 + s], bin = Fb[516 + s + 1u] - Fb[516 + s];
+        const u64 rice = sums ? Fb[s] : Fb[s + 1u] - Fb[s];
+        const u64 zr = sums ? Fb[258 + s] : Fb[258 + s + 1u] - Fb[258 + s];
+        const u64 bin = sums ? Fb[516 + s] : Fb[516 + s + 1u] - Fb[516 + s];
         const bool hr = (mi->hasrun_bits[s >> 5] >> (s & 31u)) & 1u;
         const uint32_t kk = sm.SegK()[sid];
         const u64 sbits = sm.SegStat()[sid];
@@ -513,9 +525,13 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
         if (bin < bits) { mode = MODE_BIN; bits = bin; }
         if (sbits < bits || sbits <= bits + bits / 20ull) { mode = MODE_STATIC; k = kk >> 8; bits = sbits; }  // :518, :190-192
         sm.SelMK()[sid] = (uint8_t)((mode << 5) | k);
-        part_sum += bits;
+        SelBits[s] = bits;
       }
-      const u64 sum_bits = block_sum_u64<NT, E>(sm, part_sum);
+      __syncthreads();
+      // every warp adds up the (at most 256) segment costs itself: one barrier instead of a block reduction
+      u64 part_sum = 0ull;
+      for (uint32_t s = tid & 31u; s < cnt; s += 32u) part_sum += SelBits[s];
+      const u64 sum_bits = warp_sum_u64(part_sum);
       u64 total = sum_bits + 8ull + 7ull * cnt;
       total += (8ull - (total & 7ull)) & 7ull;
       const u64 margin = best_total / 20ull;

@@ -885,10 +885,20 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     mi->tot_bin = 0ull;
   }
   if (tid < 8) mi->hasrun_bits[tid] = 0u;
+  // Full blocks: every chunk lies inside one segment and segments are whole groups of threads, so the
+  // per-segment sums are accumulated directly (Fb as 3 x 258 sums) instead of through three block scans.
+  const bool direct = !STATEFUL && n == (uint32_t)(NT * E);
+  if (direct && tid < (1u << p)) {
+    u64* Fz = sm.Fb();
+    Fz[tid] = 0ull;
+    Fz[258 + tid] = 0ull;
+    Fz[516 + tid] = 0ull;
+  }
   k_series<NT, E, STATEFUL>(sm, pr, n, sg);  // ends with a barrier
   uint32_t kinitA, kinitB = 0u;
   if (STATEFUL) {
-    kinitA = kinit_stateful;
+    kinitA = mi->k_init;  // published by the last warp before the barriers inside k_series
+    (void)kinit_stateful;
   } else {
     kinitA = sm.SegK()[sg.sidA] & 0xFFu;
     if (sg.bnd != 0xFFFFFFFFu) kinitB = sm.SegK()[sg.sidA + 1u] & 0xFFu;
@@ -988,6 +998,36 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     const uint32_t any_run = (uint32_t)__syncthreads_or((int)runA);  // also publishes the totals
     LACB_PH(11);
     return any_run;
+  } else if (direct) {
+    u64* Fb = sm.Fb();
+    LACB_PH(10);
+    const uint32_t per_seg = (uint32_t)NT >> p;  // threads per segment: 512 ... 4
+    u64 a = riceA, b = zrA, c = binA;
+    uint32_t run = runA;
+    if (per_seg >= 32u) {
+      a = warp_sum_u64(a);
+      b = warp_sum_u64(b);
+      c = warp_sum_u64(c);
+      run = __reduce_or_sync(kFull, run);
+    } else {
+      for (uint32_t d = per_seg >> 1; d > 0u; d >>= 1) {  // groups of 16 / 8 / 4 lanes
+        a += __shfl_xor_sync(kFull, a, (int)d);
+        b += __shfl_xor_sync(kFull, b, (int)d);
+        c += __shfl_xor_sync(kFull, c, (int)d);
+        run |= __shfl_xor_sync(kFull, run, (int)d);
+      }
+    }
+    const uint32_t lead = per_seg >= 32u ? 31u : per_seg - 1u;
+    if ((tid & lead) == 0u) {
+      atomicAdd(&Fb[sg.s0], a);
+      if (pr.any4) atomicAdd(&Fb[258 + sg.s0], b);
+      atomicAdd(&Fb[516 + sg.s0], c);
+      if (run) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
+    }
+    LACB_PH(14);
+    __syncthreads();
+    LACB_PH(15);
+    return 1u;  // Fb holds sums, not prefixes
   } else {
     u64* Fb = sm.Fb();
     const uint32_t cnt = 1u << p;

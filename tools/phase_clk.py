@@ -7,13 +7,13 @@ lib = sys.argv[1]; secs = int(sys.argv[2]) if len(sys.argv) > 2 else 120
 cd = H.lacb_module().Codec(0, lib)
 dll = C.CDLL(lib)
 l, r, pk = H.synth(2, 96000 * secs, 24, want_packed=True)
-buf = (C.c_ulonglong * 64)()
+buf = (C.c_ulonglong * 160)()
 cd.encode_blocks(None, None, 24, 1, packed=pk, channels=2)
 dll.lacb_debug_phase_clk(buf, 1)
 cd.encode_blocks(None, None, 24, 1, packed=pk, channels=2)
 dll.lacb_debug_phase_clk(buf, 1)
 v = np.array(buf[:], dtype=np.float64)
-tot = v.sum()
+tot = v[:64].sum()
 names = {0: "load_block", 1: "residual(+loop top)", 2: "prepare->scan", 3: "wait scan", 4: "prepare rest", 5: "wait any4",
          6: "static k + kbase/flags", 7: "wait flg", 8: "bias / k store", 9: "wait K", 10: "walk+reduce", 11: "wait totals",
          12: "seg tables", 13: "wait seg", 14: "level scans", 15: "wait level", 16: "level select", 17: "final size", 18: "final sum"}
@@ -22,3 +22,6 @@ for base, tag in ((0, "candidates"), (20, "levels/final")):
     for i in range(20):
         if v[base + i]:
             print(f"{tag:13s} {i:2d} {names.get(i, ''):24s} {100 * v[base + i] / tot:6.2f}%")
+for i, nm in enumerate(("kbase/flags", "bias", "walk")):
+    w = v[64 + 32 * i: 96 + 32 * i]
+    print(f"busy per warp, {nm}: " + " ".join(f"{x / w.mean():.2f}" for x in w))
