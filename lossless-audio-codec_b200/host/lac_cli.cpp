@@ -27,7 +27,8 @@ void usage() {
             << "  lac_cli encode input.wav output.lac [--stereo-mode=lr|ms] [--threads=N] [--devices=N] "
                "[--debug-threads] [--no-partitioning] [--allow-large]\n"
             << "  lac_cli decode input.lac output.wav [--threads=N] [--debug-threads]\n"
-            << "  lac_cli selftest\n";
+            << "  lac_cli selftest\n"
+            << "  lac_cli batch list.txt        (one encode/decode command per line, one process)\n";
 }
 
 size_t parse_count_flag(const std::string& arg, const char* name) {
@@ -146,14 +147,66 @@ int selftest() {
 
 }  // namespace
 
-int main(int argc, char** argv) {
+static int run_command(int argc, char** argv);
+
+// `lac_cli batch list.txt`: one encode / decode command per line (same arguments as on the
+// command line, whitespace separated, '#' starts a comment), executed in this process.  CUDA
+// start-up (0.5 - 2 s per process) is paid once instead of once per file, which is what makes
+// the GPU path worthwhile for collections of short files.  Exit status 1 if any line failed.
+static int run_batch(const char* argv0, const char* list_path) {
+  FILE* f = std::fopen(list_path, "r");
+  if (!f) {
+    std::cerr << "Failed to read batch list: " << list_path << "\n";
+    return 1;
+  }
+  int failures = 0;
+  char line[8192];
+  while (std::fgets(line, sizeof line, f)) {
+    std::vector<std::string> words;
+    std::string cur;
+    for (const char* p = line; *p && *p != '#'; ++p) {
+      if (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') {
+        if (!cur.empty()) words.push_back(cur);
+        cur.clear();
+      } else {
+        cur.push_back(*p);
+      }
+    }
+    if (!cur.empty()) words.push_back(cur);
+    if (words.empty()) continue;
+    if (words[0] == "batch") {
+      std::cerr << "batch lists do not nest\n";
+      ++failures;
+      continue;
+    }
+    std::vector<char*> av;
+    av.push_back(const_cast<char*>(argv0));
+    for (std::string& w : words) av.push_back(w.data());
+    if (run_command((int)av.size(), av.data()) != 0) ++failures;
+  }
+  std::fclose(f);
+  return failures ? 1 : 0;
+}
+
+// LAC_TIMING=1: wall-clock milestones on stderr (where a short run spends its time)
+static void milestone(const char* what) {
+  static const bool on = std::getenv("LAC_TIMING") != nullptr;
+  static const auto t0 = std::chrono::steady_clock::now();
+  if (on)
+    std::cerr << "[lac_cli " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()
+              << " ms] " << what << "\n";
+}
+
+static int run_command(int argc, char** argv) {
   try {
+    milestone("start");
     if (argc < 2) {
       usage();
       return 1;
     }
     const std::string cmd = argv[1];
     if (cmd == "selftest") return selftest();
+    if (cmd == "batch" && argc == 3) return run_batch(argv[0], argv[2]);
     if ((cmd != "encode" && cmd != "decode") || argc < 4) {
       usage();
       return 1;
@@ -192,17 +245,20 @@ int main(int argc, char** argv) {
         std::cerr << "Failed to read WAV: " << in_path << "\n";
         return 1;
       }
+      milestone("wav read");
       LAC::ThreadCollector tc;
       LAC::Encoder enc(12, stereo_mode, info.sample_rate, info.bit_depth);
       enc.set_partitioning_enabled(partitioning);
       enc.set_thread_count(threads);
       enc.set_device_count(devices);
       const std::vector<uint8_t> bitstream = enc.encode_packed(pcm.data(), info.frames, (uint8_t)info.channels, &tc);
+      milestone("encoded");
       Staged st(out_path);
       if (!st.ok || !save_file(st.tmp_path.string(), bitstream) || !st.publish()) {
         std::cerr << "Failed to write LAC file: " << out_path << "\n";
         return 1;
       }
+      milestone("lac written");
       std::cout << "Encoded " << in_path << " -> " << out_path << " (" << bitstream.size() << " bytes)\n";
       if (debug_threads) print_threads("Thread usage", tc);
       return 0;
@@ -213,6 +269,7 @@ int main(int argc, char** argv) {
       std::cerr << "Failed to read LAC file: " << in_path << "\n";
       return 1;
     }
+    milestone("lac read");
     LAC::ThreadCollector tc;
     LAC::Decoder dec(&tc);
     dec.set_thread_count(threads);
@@ -225,6 +282,7 @@ int main(int argc, char** argv) {
       std::cerr << "Decode failed: " << e.what() << "\n";
       return 1;
     }
+    milestone("decoded");
     WavInfo info;
     info.channels = hdr.channels;
     info.sample_rate = hdr.sample_rate;
@@ -235,6 +293,7 @@ int main(int argc, char** argv) {
       std::cerr << "Failed to write WAV: " << out_path << "\n";
       return 1;
     }
+    milestone("wav written");
     std::cout << "Decoded " << in_path << " -> " << out_path << " (" << frames << " samples per channel)\n";
     if (debug_threads) print_threads("Decoder thread usage", tc);
     return 0;
@@ -243,3 +302,5 @@ int main(int argc, char** argv) {
     return 1;
   }
 }
+
+int main(int argc, char** argv) { return run_command(argc, argv); }

@@ -81,3 +81,28 @@ def test_cli_rejections(cli, tmp_path):
     res = _run(cli, "decode", str(tmp_path / "broken.lac"), str(tmp_path / "o.wav"))
     assert res.returncode == 1 and "Decode failed: [decode-error]" in res.stderr and not (tmp_path / "o.wav").exists()
     assert not [p for p in os.listdir(tmp_path) if ".tmp." in p]                       # no staged leftovers
+
+
+def test_batch_mode(cli, tmp_path):
+    """`lac_cli batch list.txt` runs many commands in one process (CUDA start-up paid once); results
+    are those of the one-shot commands, a failing line gives exit status 1 but does not stop the rest."""
+    lines = []
+    want = {}
+    for i, (depth, rate) in enumerate(((16, 44100), (24, 48000), (24, 96000))):
+        l, r, pk = H.synth(20 + i, 2 * 16384 + 311 * i, depth, want_packed=True)
+        wav = tmp_path / f"in{i}.wav"
+        _write_wav(wav, pk, 2, rate, depth)
+        lines.append(f"encode {wav} {tmp_path / f'o{i}.lac'}   # file {i}")
+        lines.append(f"decode {tmp_path / f'o{i}.lac'} {tmp_path / f'b{i}.wav'}")
+        want[i] = (H.oracle().encode(l, r, rate, depth, 2), wav.read_bytes())
+    lst = tmp_path / "list.txt"
+    lst.write_text("\n".join(lines) + "\n\n")
+    res = _run(cli, "batch", str(lst))
+    assert res.returncode == 0, res.stderr
+    for i, (lac, wav) in want.items():
+        assert (tmp_path / f"o{i}.lac").read_bytes() == lac
+        assert (tmp_path / f"b{i}.wav").read_bytes() == wav
+    lst.write_text(f"decode {tmp_path / 'missing.lac'} {tmp_path / 'x.wav'}\n" + lines[0] + "\n")
+    (tmp_path / "o0.lac").unlink()
+    res = _run(cli, "batch", str(lst))
+    assert res.returncode == 1 and (tmp_path / "o0.lac").exists()
