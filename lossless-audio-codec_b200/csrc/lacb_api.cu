@@ -155,7 +155,7 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
     LACB_LAUNCH(kp, lacb_umin(nb, (uint32_t)ctx->sms * 8u), 256, 0, st, src, cfg, as<uint32_t>(ctx->flags));
     auto kb = k_build_jobs<true>;
     LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs_p), counts + 1);
-    const uint32_t pgrid = lacb_umin(nb * 12u, (uint32_t)ctx->sms * 16u);
+    const uint32_t pgrid = lacb_umin(nb * 12u, (uint32_t)ctx->sms * 32u);
     auto ka = k_autocorr<PROBE_NT, PROBE_E, true>;
     LACB_LAUNCH(ka, pgrid, PROBE_NT, PROBE_NT * PROBE_E * 4, st, src, as<uint32_t>(ctx->jobs_p), counts + 1,
                 as<i64>(ctx->acor_p));

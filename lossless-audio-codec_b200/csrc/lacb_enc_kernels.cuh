@@ -330,7 +330,7 @@ __device__ __forceinline__ bool compute_residual(const int32_t (&x)[E + 12], uin
 }
 
 template <int NT, int E, bool PROBE>
-__global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
+__global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
                                                 const LpcQ* lpcq, ChanRec* recs, uint32_t* probe_bytes) {
   LACB_DYN_SMEM(unsigned char, smraw);
   ASmem<NT, E> sm{smraw};
@@ -514,8 +514,8 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 16 : 1)) k_analyze(PcmSrc src,
       for (uint32_t s = tid; s < cnt; s += NT) {
         const uint32_t sid = cnt - 1u + s;
         const u64 rice = sums ? Fb[s] : Fb[s + 1u] - Fb[s];
-        const u64 zr = sums ? Fb[258 + s] : Fb[258 + s + 1u] - Fb[258 + s];
-        const u64 bin = sums ? Fb[516 + s] : Fb[516 + s + 1u] - Fb[516 + s];
+        const u64 zr = sums ? Fb[ASmem<NT, E>::FBS + s] : Fb[ASmem<NT, E>::FBS + s + 1u] - Fb[ASmem<NT, E>::FBS + s];
+        const u64 bin = sums ? Fb[2u * ASmem<NT, E>::FBS + s] : Fb[2u * ASmem<NT, E>::FBS + s + 1u] - Fb[2u * ASmem<NT, E>::FBS + s];
         const bool hr = (mi->hasrun_bits[s >> 5] >> (s & 31u)) & 1u;
         const uint32_t kk = sm.SegK()[sid];
         const u64 sbits = sm.SegStat()[sid];

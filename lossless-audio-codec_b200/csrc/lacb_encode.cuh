@@ -81,7 +81,12 @@ struct AMisc {
 template <int NT, int E>
 struct ASmem {
   static constexpr uint32_t CAP = NT * E;
-  static constexpr uint32_t MAXSEG = 511;
+  // partition tables are sized for the block capacity: 16384 samples -> levels 0..8 (511 segments),
+  // a 256-sample probe -> levels 0..3 (15 segments); small tables let many probe CTAs share an SM
+  static constexpr uint32_t MAXP = CAP >= 8192u ? 8u : CAP >= 4096u ? 7u : CAP >= 2048u ? 6u : CAP >= 1024u ? 5u
+                                   : CAP >= 512u ? 4u : CAP >= 256u ? 3u : CAP >= 128u ? 2u : CAP >= 64u ? 1u : 0u;
+  static constexpr uint32_t MAXSEG = (2u << MAXP) - 1u;
+  static constexpr uint32_t FBS = (1u << MAXP) + 2u;  // stride of the three per-segment cost arrays
   static constexpr size_t oX = 0;
   static constexpr size_t oU = oX + (size_t)CAP * 4;
   static constexpr size_t oPthr = oU + (size_t)CAP * 4;
@@ -93,7 +98,7 @@ struct ASmem {
   static constexpr size_t oSegStat = oSegP + (MAXSEG + 1) * 8;
   static constexpr size_t oSelBits = oSegStat + (MAXSEG + 1) * 8;
   static constexpr size_t oFb = oSelBits + (MAXSEG + 1) * 8;
-  static constexpr size_t oMisc = oFb + 3 * 258 * 8;
+  static constexpr size_t oMisc = oFb + 3 * (size_t)FBS * 8;
   static constexpr size_t oSegK = oMisc + ((sizeof(AMisc) + 15) & ~(size_t)15);
   static constexpr size_t oSelMK = oSegK + (MAXSEG + 1) * 2;
   static constexpr size_t BYTES = oSelMK + (MAXSEG + 1);
@@ -871,7 +876,7 @@ __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT
 }
 
 // estimate_residual_costs (block/encoder.cpp:201-263) for one level.  STATEFUL writes
-// block totals to AMisc; otherwise per-segment prefix values go to Fb (3 x 258) and
+// block totals to AMisc; otherwise per-segment prefix values go to Fb (three arrays) and
 // the has-run bits to AMisc::hasrun_bits.
 template <int NT, int E, bool STATEFUL>
 __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t p,
@@ -886,13 +891,13 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
   }
   if (tid < 8) mi->hasrun_bits[tid] = 0u;
   // Full blocks: every chunk lies inside one segment and segments are whole groups of threads, so the
-  // per-segment sums are accumulated directly (Fb as 3 x 258 sums) instead of through three block scans.
+  // per-segment sums are accumulated directly (Fb as three arrays of sums) instead of through three block scans.
   const bool direct = !STATEFUL && n == (uint32_t)(NT * E);
   if (direct && tid < (1u << p)) {
     u64* Fz = sm.Fb();
     Fz[tid] = 0ull;
-    Fz[258 + tid] = 0ull;
-    Fz[516 + tid] = 0ull;
+    Fz[ASmem<NT, E>::FBS + tid] = 0ull;
+    Fz[2u * ASmem<NT, E>::FBS + tid] = 0ull;
   }
   k_series<NT, E, STATEFUL>(sm, pr, n, sg);  // ends with a barrier
   uint32_t kinitA, kinitB = 0u;
@@ -1020,8 +1025,8 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     const uint32_t lead = per_seg >= 32u ? 31u : per_seg - 1u;
     if ((tid & lead) == 0u) {
       atomicAdd(&Fb[sg.s0], a);
-      if (pr.any4) atomicAdd(&Fb[258 + sg.s0], b);
-      atomicAdd(&Fb[516 + sg.s0], c);
+      if (pr.any4) atomicAdd(&Fb[ASmem<NT, E>::FBS + sg.s0], b);
+      atomicAdd(&Fb[2u * ASmem<NT, E>::FBS + sg.s0], c);
       if (run) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
     }
     LACB_PH(14);
@@ -1040,13 +1045,13 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     if (ownsB) Fb[sg.s0 + 1u] = ex + riceA;
     if (tid == 0) Fb[cnt] = tot;
     ex = block_excl_scan_u64<NT>(zrA + zrB, sm.Scr(), &tot);
-    if (ownsA) Fb[258 + sg.s0] = ex;
-    if (ownsB) Fb[258 + sg.s0 + 1u] = ex + zrA;
-    if (tid == 0) Fb[258 + cnt] = tot;
+    if (ownsA) Fb[ASmem<NT, E>::FBS + sg.s0] = ex;
+    if (ownsB) Fb[ASmem<NT, E>::FBS + sg.s0 + 1u] = ex + zrA;
+    if (tid == 0) Fb[ASmem<NT, E>::FBS + cnt] = tot;
     ex = block_excl_scan_u64<NT>(binA + binB, sm.Scr(), &tot);
-    if (ownsA) Fb[516 + sg.s0] = ex;
-    if (ownsB) Fb[516 + sg.s0 + 1u] = ex + binA;
-    if (tid == 0) Fb[516 + cnt] = tot;
+    if (ownsA) Fb[2u * ASmem<NT, E>::FBS + sg.s0] = ex;
+    if (ownsB) Fb[2u * ASmem<NT, E>::FBS + sg.s0 + 1u] = ex + binA;
+    if (tid == 0) Fb[2u * ASmem<NT, E>::FBS + cnt] = tot;
     if (runA) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
     if (runB) atomicOr(&mi->hasrun_bits[(sg.s0 + 1u) >> 5], 1u << ((sg.s0 + 1u) & 31u));
     LACB_PH(14);
