@@ -96,6 +96,8 @@ def test_gpu_frames_match_golden():
 
 @pytest.mark.gpu
 def test_gpu_synthetic_match_golden():
+    """Includes BASELINE configs[1] at its full size: 600 s of 24-bit / 96 kHz stereo, forced mid/side,
+    345.6 MB of PCM -> the reference's 213 135 210 bytes, SHA-256 recorded from the unmodified reference."""
     _check_synthetic(H.gpu_codec(), sorted(GOLD["synthetic"].keys()))
 
 

@@ -49,9 +49,10 @@ def main():
         "C2_10s_24_96k_ms": (2, 960000, 24, 96000, 2, 1),
         "C3_5s_24_192k_mono": (3, 960000, 24, 192000, 1, 0),
         "C4_10s_24_48k_auto": (4, 480000, 24, 48000, 2, 2),
+        "C2_full_600s_24_96k_ms": (2, 57600000, 24, 96000, 2, 1),  # BASELINE configs[1] at full size (213 135 210 bytes)
     }.items():
         l, r = H.synth(seed, frames, depth, ch)
-        b = ref.encode(l, r if ch == 2 else None, rate, depth, mode)
+        b = ref.encode(l, r if ch == 2 else None, rate, depth, mode, threads=8)
         out["synthetic"][key] = dict(digest(bytes(b)), seed=seed, frames=frames, depth=depth, rate=rate,
                                      channels=ch, stereo_mode=mode)
     # a few short streams verbatim, so a mismatch can be diffed without the reference
