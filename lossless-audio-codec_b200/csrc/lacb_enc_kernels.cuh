@@ -403,14 +403,12 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       Prep<NT, E> pr;
       LACB_PH(1);
       prepare<NT, E, false>(sm, r, n, pr);
-#ifndef LACB_X_NOPRUNE
       if (mi->best.have && (u64)mi->lb > mi->best.best) {
         // cannot beat (or tie) the best candidate so far: skip its adaptive-k evaluation
         if (!PROBE && tid == 0u) recs[slot].cand_lo[ci] = 0xFFFFFFFEu;
         __syncthreads();  // everyone has read lb / best before the next candidate resets them
         continue;
       }
-#endif
       // initial / static k of the whole block from the block totals, one k per lane.  Only thread 0
       // consumes them (two barriers later), so the last warp -- on average the least loaded one, the
       // first warps carry the block start where k moves most -- evaluates them for everybody.
@@ -459,11 +457,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     LACB_PH(1);
     prepare<NT, E, true>(sm, r, n, pr);
 
-#ifdef LACB_X_NOLEVELS
-    const uint32_t max_p = 0u;
-#else
     const uint32_t max_p = (cfg.partitioning && n >= kMinPart) ? max_partition_order(n) : 0u;
-#endif
     // per-segment initial k, static k / bits and prefix of u, all levels at once
     for (uint32_t sid = tid; sid < (2u << max_p) - 1u; sid += NT) {
       const uint32_t p = 31u - (uint32_t)__clz((int)(sid + 1u));

@@ -377,12 +377,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   if (NT * E > 256 && g0 == 256u) mi->p_first = pr.Pex;
 
   PlaneCounts pc;
-#ifdef LACB_X_NOPREP
-  for (int w = 0; w < 8; ++w) pc.w[w] = V[w % 5];
-  if (!FULL) { pr.any4 = (uint32_t)__syncthreads_or(0); return; }
-#else
   planes_from_sliced(V, pc);
-#endif
   if (FULL) {
     PlaneCounts* Cp = sm.Cpre();
 #pragma unroll
@@ -501,9 +496,6 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
       const u64 lo = (1ull << (kb0 - 1u)) + 1ull, hi = (1ull << kb0) + 1ull;
       uniform = (N_first >= lo * c_last) && (kb0 == 31u || N_last < hi * c_first);
     }
-#ifdef LACB_X_NOKSER
-    uniform = true;
-#endif
     if (uniform) {
 #pragma unroll
       for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = kb0 * 0x01010101u;
@@ -590,9 +582,6 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
   const uint32_t part = ((int)tid - D >= 0) ? Flg[tid - D] : 0u;
   const int tt = (int)tid - DW;
   u64 wprev = tt >= 0 ? sm.Pthr()[tt] : 0ull;  // becomes the inclusive prefix at item j of thread tt
-#ifdef LACB_X_NOBIAS
-  return;
-#endif
   const uint32_t c_first = g0 + 1u, c_last = g0 + (uint32_t)E;
   // exact window counts over the 96 samples before item 0
   const uint32_t L0 = fullL + (uint32_t)__popc(part & 0xFFFFu), Z0 = fullZ + (uint32_t)__popc(part >> 16);
@@ -863,9 +852,6 @@ template <int NT, int E, typename F>
 __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                            const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
   if (threadIdx.x * E >= n) return;
-#ifdef LACB_X_NOWALK
-  return;
-#endif
   if (pr.any4) {
     if (sg.fast) walk_thread<NT, E, true, true>(sm, pr, n, sg, kinitA, kinitB, f);
     else walk_thread<NT, E, false, true>(sm, pr, n, sg, kinitA, kinitB, f);
@@ -915,9 +901,6 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
   // exactly two bits more per sample unless a zero-run escape (u > 8 << k, i.e. some q >= 8
   // here) can occur; those and all other chunks take the general walk.
   bool plain = sg.fast && !(pr.cls & 1u) && (pr.cls >> 8) <= 24u;
-#ifdef LACB_X_NOWALK
-  plain = false;
-#endif
   if (plain) {
     uint32_t u[E];
     load_u<NT, E>(sm, u);
