@@ -75,6 +75,7 @@ struct AMisc {
   uint32_t cnt_tot[8], cnt_first[8];
   uint32_t k_init, k_stat, has_run, red32;
   uint32_t lb;  // lower bound of the candidate's cost (see prepare)
+  uint32_t hq_n;  // entries in the hard-chunk queue
   uint32_t hasrun_bits[8];
 };
 
@@ -101,7 +102,8 @@ struct ASmem {
   static constexpr size_t oMisc = oFb + 3 * (size_t)FBS * 8;
   static constexpr size_t oSegK = oMisc + ((sizeof(AMisc) + 15) & ~(size_t)15);
   static constexpr size_t oSelMK = oSegK + (MAXSEG + 1) * 2;
-  static constexpr size_t BYTES = oSelMK + (MAXSEG + 1);
+  static constexpr size_t oHardQ = (oSelMK + (MAXSEG + 1) + 15) & ~(size_t)15;
+  static constexpr size_t BYTES = oHardQ + (size_t)NT * 2;
 
   unsigned char* base;
   __device__ int32_t* X() const { return reinterpret_cast<int32_t*>(base + oX); }
@@ -118,6 +120,7 @@ struct ASmem {
   __device__ AMisc* Misc() const { return reinterpret_cast<AMisc*>(base + oMisc); }
   __device__ uint16_t* SegK() const { return reinterpret_cast<uint16_t*>(base + oSegK); }
   __device__ uint8_t* SelMK() const { return reinterpret_cast<uint8_t*>(base + oSelMK); }
+  __device__ uint16_t* HardQ() const { return reinterpret_cast<uint16_t*>(base + oHardQ); }  // chunks awaiting k_bias_pair
 };
 
 // ---------------------------------------------------------------------------
@@ -564,8 +567,10 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) { return ((w + 0x7
 //    stationary signals, by a 16-step count over two flag words.
 // The bias is then applied to the four packed k words with byte-parallel arithmetic.
 // Chunks where a bound fails (level changes, block start) run the exact per-sample loop.
-template <int NT, int E, bool FAST>
-__device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t flg,
+// Returns true when kpk holds the biased k of the chunk.  With SLOW = false a chunk that needs the
+// per-sample evaluation is left untouched and false is returned (the caller queues it for k_bias_pair).
+template <int NT, int E, bool SLOW>
+__device__ __forceinline__ bool k_bias_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t flg,
                                               uint32_t (&kpk)[E / 4]) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
   const uint32_t* Flg = sm.Flg();
@@ -684,10 +689,11 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
           k = k < 0 ? 0 : (k > 31 ? 31 : k);
           kpk[E / 4 - 1] = (kpk[E / 4 - 1] & 0x00FFFFFFu) | ((uint32_t)k << 24);
         }
-        return;
+        return true;
       }
     }
   }
+  if (!SLOW) return false;
   uint32_t u[E];
   load_u<NT, E>(sm, u);
   const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
@@ -730,6 +736,72 @@ __device__ __forceinline__ void k_bias_thread(const ASmem<NT, E>& sm, const Prep
     k = k < 0 ? 0 : (k > 31 ? 31 : k);
     kpk[j >> 2] = (kpk[j >> 2] & ~(0xFFu << (8 * (j & 3)))) | ((uint32_t)k << (8 * (j & 3)));
   }
+  return true;
+}
+
+// The exact per-sample bias of two chunks at once, one lane per sample (lanes 0..15: chunk tA, lanes
+// 16..31: chunk tB; an id >= NT means "none").  Chunks that k_bias_thread could not settle with its
+// chunk-level proofs are collected block-wide and dealt to the warps in pairs, so the cost of the hard
+// chunks (level changes, block start) is spread over all 32 warps instead of stalling the barrier behind
+// the few warps that own them.  Reads the base k bytes of the chunk from the K plane and replaces them by
+// the biased k; same arithmetic as the per-sample loop above (rice.hpp:60-112).
+template <int NT, int E>
+__device__ __forceinline__ void k_bias_pair(const ASmem<NT, E>& sm, uint32_t tA, uint32_t tB) {
+  constexpr uint32_t D = kMicroWin / E, DW = kDriftWin / E;
+  const uint32_t lane = threadIdx.x & 31u, j = lane & 15u;
+  const uint32_t t = lane < 16u ? tA : tB;
+  const bool live = t < (uint32_t)NT;
+  const uint32_t tc = live ? t : 0u;  // idle half-warps follow along on chunk 0 and drop the result
+  const uint32_t g0 = tc * E;
+  const uint32_t* U = sm.U();
+  const uint32_t u = U[swz(g0 + j)];
+  const bool has_w = tc >= DW;
+  const uint32_t u2 = has_w ? U[swz((tc - DW) * E + j)] : 0u;
+  u64 p1 = u, p2 = u2;  // inclusive prefixes inside the chunk and inside the chunk leaving the drift window
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const u64 y1 = __shfl_up_sync(kFull, p1, d, 16), y2 = __shfl_up_sync(kFull, p2, d, 16);
+    if (j >= (uint32_t)d) {
+      p1 += y1;
+      p2 += y2;
+    }
+  }
+  const u64 Pin = sm.Pthr()[tc] + p1;
+  const u64 wprev = has_w ? sm.Pthr()[tc - DW] + p2 : 0ull;
+  const uint32_t c = g0 + j + 1u;
+  const u64 N = Pin + (c >> 1);
+  uint8_t* Kb = reinterpret_cast<uint8_t*>(sm.Kpl());
+  const uint32_t kb = Kb[g0 + j];
+  int bias = 0;
+  if (c >= kDriftWin && N >= (u64)c) {
+    const u64 lm = (Pin - wprev + 128ull) >> 8;
+    const u64 tA2 = (3ull * lm + 3ull) >> 2;
+    if (N < tA2 * c) {
+      bias = 1;
+    } else {
+      const u64 tB2 = lm + 2ull + lm / 3ull;
+      if (N >= tB2 * c) bias = -1;
+    }
+  }
+  if (c >= kMicroWin) {
+    const uint32_t* Flg = sm.Flg();
+    uint32_t L = 0u, Z = 0u;
+#pragma unroll
+    for (uint32_t d = 1; d <= D; ++d) {  // the 96 samples before item 0: threads t-6 .. t-1
+      const uint32_t w = tc >= d ? Flg[tc - d] : 0u;
+      L += (uint32_t)__popc(w & 0xFFFFu);
+      Z += (uint32_t)__popc(w >> 16);
+    }
+    const uint32_t own = Flg[tc], part = tc >= D ? Flg[tc - D] : 0u;
+    const uint32_t m = (2u << j) - 1u;  // items 0..j have entered, the same items of thread t-6 have left
+    L += (uint32_t)__popc(own & m) - (uint32_t)__popc(part & m);
+    Z += (uint32_t)__popc((own >> 16) & m) - (uint32_t)__popc((part >> 16) & m);
+    if (L * 4u >= 288u) bias = bias + 1 < 1 ? bias + 1 : 1;
+    else if (Z * 5u >= 384u) bias = bias - 1 > -1 ? bias - 1 : -1;
+  }
+  int k = (int)kb + bias;
+  k = k < 0 ? 0 : (k > 31 ? 31 : k);
+  if (live) Kb[g0 + j] = (uint8_t)k;
 }
 
 template <int NT, int E, bool STATEFUL>
@@ -740,16 +812,39 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
   uint32_t flg;
   if (sg.fast) k_series_thread<NT, E, STATEFUL, true>(sm, pr, n, sg, kpk, flg);
   else k_series_thread<NT, E, STATEFUL, false>(sm, pr, n, sg, kpk, flg);
+  uint32_t* K = sm.Kpl() + tid * (E / 4);
   if (STATEFUL) {
+    constexpr bool COOP = (NT >= 64) && (E == 16);  // several warps to share the hard chunks between
+    AMisc* mi = sm.Misc();
     sm.Flg()[tid] = flg;
+    if (COOP && tid == 0u) mi->hq_n = 0u;
     LACB_PH(6);
     __syncthreads();
     LACB_PH(7);
-    k_bias_thread<NT, E, true>(sm, pr, flg, kpk);
-  }
-  uint32_t* K = sm.Kpl() + tid * (E / 4);
+    const bool done = k_bias_thread<NT, E, !COOP>(sm, pr, flg, kpk);
 #pragma unroll
-  for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];
+    for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];  // biased k, or the base k of a chunk left for the pairs
+    if constexpr (COOP) {
+      uint16_t* hq = sm.HardQ();
+      const uint32_t lane = tid & 31u;
+      const uint32_t hm = __ballot_sync(kFull, !done);
+      if (hm) {  // one shared-memory atomic per warp
+        uint32_t base = 0u;
+        if (lane == 0u) base = atomicAdd(&mi->hq_n, (uint32_t)__popc(hm));
+        base = __shfl_sync(kFull, base, 0);
+        if (!done) hq[base + (uint32_t)__popc(hm & ((1u << lane) - 1u))] = (uint16_t)tid;
+      }
+      LACB_PH(8);
+      __syncthreads();
+      LACB_PH(9);
+      const uint32_t nh = mi->hq_n;
+      for (uint32_t i = (tid >> 5) * 2u; i < nh; i += (uint32_t)(NT / 32) * 2u)
+        k_bias_pair<NT, E>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu);
+    }
+  } else {
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];
+  }
   LACB_PH(8);
   __syncthreads();
   LACB_PH(9);
