@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     if (!PROBE && tid < 11u) recs[slot].cand_lo[tid] = 0xFFFFFFFFu;
 
     if (tid == 0u) mi->best.have = 0u;  // ordered before its first use by the barriers of the first candidate
+    if (tid == 0u) mi->hq_kb_n = 0u;
     // candidate order: fixed 0..4, FIR, LPC 4,6,8,10,12 (block/encoder.cpp:362-407)
     for (uint32_t ci = 0; ci < 11u; ++ci) {
       int32_t r[E];
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       const uint8_t* mk = sm.SelMK();
       const uint32_t mkA = mk[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? mk[sg.sidA + 1u] : 0u;
       if (best_p == 0u) k_series<NT, E, true>(sm, pr, n, sg);
-      else k_series<NT, E, false>(sm, pr, n, sg);
+      else k_series<NT, E, false>(sm, pr, n, sg, best_p);
       walk_items<NT, E>(sm, pr, n, sg, mkA & 31u, mkB & 31u,
                         [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes,
                             bool long_run) {
@@ -680,6 +681,7 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
     if (flagged && ch == 0u && tid == 0u) payload[blk_off[b]] = (f & BF_CHOOSE_MS) ? 1 : 0;
 
     LACB_PH_INIT(-1);
+    if (tid == 0u) sm.Misc()->hq_kb_n = 0u;
     load_block<NT, E>(sm, src, (int)(s0 + ch), (u64)b * kMaxBlock, n);
     __syncthreads();
     int32_t x[E + 12];
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
     const SegGeom sg = seg_geom<E>(g0, n, p);
     const uint32_t mkA = sm.SelMK()[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? sm.SelMK()[sg.sidA + 1u] : 0u;
     if (p == 0u) k_series<NT, E, true>(sm, pr, n, sg);
-    else k_series<NT, E, false>(sm, pr, n, sg);
+    else k_series<NT, E, false>(sm, pr, n, sg, p);
     u64 my_bits = 0ull;
     walk_items<NT, E>(sm, pr, n, sg, mkA & 31u, mkB & 31u,
                       [&](int, uint32_t, bool inB, uint32_t u, uint32_t k, bool is_zero, uint32_t closes, bool long_run) {

@@ -75,7 +75,7 @@ struct AMisc {
   uint32_t cnt_tot[8], cnt_first[8];
   uint32_t k_init, k_stat, has_run, red32;
   uint32_t lb;  // lower bound of the candidate's cost (see prepare)
-  uint32_t hq_n;  // entries in the hard-chunk queue
+  uint32_t hq_n, hq_kb_n;  // entries in the hard-chunk queue (bias pairs / base-k pairs)
   uint32_t hasrun_bits[8];
 };
 
@@ -470,8 +470,10 @@ __device__ __forceinline__ SegGeom seg_geom(uint32_t g0, uint32_t n, uint32_t p)
 // that sample starts a segment).
 //   STATEFUL  : Rice::adapt_k with drift and micro windows (rice.hpp:45-114), p = 0
 //   !STATEFUL : adapt_k_stateless (block/encoder.cpp:72-77), restarted per segment
-template <int NT, int E, bool STATEFUL, bool FAST>
-__device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+// Returns false only with DEFER: the chunk's k moves inside it and fits the 32-bit path; nothing was
+// computed and the caller queues the chunk for k_base_pair.
+template <int NT, int E, bool STATEFUL, bool FAST, bool DEFER>
+__device__ __forceinline__ bool k_series_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                                 const SegGeom& sg, uint32_t (&kpk)[E / 4], uint32_t& flg_out) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
   uint32_t u[E];
@@ -510,11 +512,15 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
         }
       }
       flg_out = flg;
-      return;
+      return true;
     }
     if (N_last < 0x80000000ull) {
       // k moves inside the chunk (block / segment start, level change): per-sample closed form,
       // in 32-bit arithmetic when the running sum allows it
+      if (DEFER) {
+        flg_out = 0u;
+        return false;
+      }
       uint32_t N32 = (uint32_t)rel;
 #pragma unroll
       for (int j = 0; j < E; ++j) {
@@ -528,7 +534,7 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
         }
       }
       flg_out = flg;
-      return;
+      return true;
     }
   }
 #pragma unroll
@@ -547,6 +553,39 @@ __device__ __forceinline__ void k_series_thread(const ASmem<NT, E>& sm, const Pr
     }
   }
   flg_out = flg;
+  return true;
+}
+
+// Base k (and the stateful model's flag words) of two chunks at once, one lane per sample: the
+// block-wide counterpart of the per-sample loop above for chunks whose k moves inside them.  Only chunks
+// that lie inside one segment and whose running sum stays below 2^31 are sent here.  Writes the k bytes
+// of the chunk to the K plane and, for the stateful model, its flag word.
+template <int NT, int E, bool STATEFUL>
+__device__ __forceinline__ void k_base_pair(const ASmem<NT, E>& sm, uint32_t tA, uint32_t tB, uint32_t n, uint32_t p) {
+  const uint32_t lane = threadIdx.x & 31u, j = lane & 15u;
+  const uint32_t t = lane < 16u ? tA : tB;
+  const bool live = t < (uint32_t)NT;
+  const uint32_t tc = live ? t : 0u;
+  const uint32_t g0 = tc * E;
+  const uint32_t u = sm.U()[swz(g0 + j)];
+  uint32_t p1 = u;
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(kFull, p1, d, 16);
+    if (j >= (uint32_t)d) p1 += y;
+  }
+  const SegGeom sg = seg_geom<E>(g0, n, STATEFUL ? 0u : p);
+  const u64 PaA = STATEFUL ? 0ull : sm.SegP()[sg.sidA];
+  const uint32_t rel = (uint32_t)(sm.Pthr()[tc] - PaA);
+  const uint32_t c = g0 + j - sg.a0 + 1u;
+  const uint32_t kb = kbase_clz32(rel + p1 + (c >> 1), c);
+  if (live) reinterpret_cast<uint8_t*>(sm.Kpl())[g0 + j] = (uint8_t)kb;
+  if (STATEFUL) {
+    const uint32_t q = u >> kb;
+    const uint32_t bl = __ballot_sync(kFull, q > 3u), bz = __ballot_sync(kFull, q == 0u);
+    const uint32_t sh = lane & 16u;
+    if (live && j == 0u) sm.Flg()[tc] = ((bl >> sh) & 0xFFFFu) | (((bz >> sh) & 0xFFFFu) << 16);
+  }
 }
 
 // 4 mask bits -> 4 bytes of 0 / 1
@@ -806,21 +845,83 @@ __device__ __forceinline__ void k_bias_pair(const ASmem<NT, E>& sm, uint32_t tA,
 
 template <int NT, int E, bool STATEFUL>
 __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
-                                         const SegGeom& sg) {
+                                         const SegGeom& sg, uint32_t p = 0u) {
   const uint32_t tid = threadIdx.x;
+  constexpr bool COOPK = (NT >= 64) && (E == 16);  // several warps to share the hard chunks between
+  AMisc* mi = sm.Misc();
   uint32_t kpk[E / 4];
   uint32_t flg;
-  if (sg.fast) k_series_thread<NT, E, STATEFUL, true>(sm, pr, n, sg, kpk, flg);
-  else k_series_thread<NT, E, STATEFUL, false>(sm, pr, n, sg, kpk, flg);
+  bool have;
+  if (sg.fast) have = k_series_thread<NT, E, STATEFUL, true, COOPK>(sm, pr, n, sg, kpk, flg);
+  else have = k_series_thread<NT, E, STATEFUL, false, false>(sm, pr, n, sg, kpk, flg);
+  if constexpr (COOPK) {
+    // chunks whose k moves inside them: queued block-wide and dealt to the warps in pairs (k_base_pair);
+    // when most chunks are like that (short segments of the deep partition levels) every owner runs the
+    // per-sample loop itself, which is the cheaper form then
+    uint16_t* hq = sm.HardQ();
+    const uint32_t lane = tid & 31u;
+    const uint32_t hm = __ballot_sync(kFull, !have);
+    if (hm) {
+      uint32_t base = 0u;
+      if (lane == 0u) base = atomicAdd(&mi->hq_kb_n, (uint32_t)__popc(hm));
+      base = __shfl_sync(kFull, base, 0);
+      if (!have) hq[base + (uint32_t)__popc(hm & ((1u << lane) - 1u))] = (uint16_t)tid;
+    }
+    if (have && !STATEFUL) {
+      uint32_t* K0 = sm.Kpl() + tid * (E / 4);
+#pragma unroll
+      for (int c4 = 0; c4 < E / 4; ++c4) K0[c4] = kpk[c4];
+    }
+    __syncthreads();
+    const uint32_t nh = mi->hq_kb_n;
+    if (nh <= (uint32_t)NT / 8u) {
+      for (uint32_t i = (tid >> 5) * 2u; i < nh; i += (uint32_t)(NT / 32) * 2u)
+        k_base_pair<NT, E, STATEFUL>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu, n, p);
+      if (STATEFUL) {
+        if (have) sm.Flg()[tid] = flg;
+        if (tid == 0u) mi->hq_n = 0u;
+        __syncthreads();
+        if (tid == 0u) mi->hq_kb_n = 0u;  // consumed; the next pushes are at least one barrier away
+        if (!have) {  // pick up what the pairs produced for this chunk
+          const uint32_t* K0 = sm.Kpl() + tid * (E / 4);
+#pragma unroll
+          for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = K0[c4];
+          flg = sm.Flg()[tid];
+        }
+      }
+    } else {
+      if (!have) {
+        k_series_thread<NT, E, STATEFUL, true, false>(sm, pr, n, sg, kpk, flg);
+        if (!STATEFUL) {
+          uint32_t* K0 = sm.Kpl() + tid * (E / 4);
+#pragma unroll
+          for (int c4 = 0; c4 < E / 4; ++c4) K0[c4] = kpk[c4];
+        }
+      }
+      if (STATEFUL) {
+        sm.Flg()[tid] = flg;
+        if (tid == 0u) mi->hq_n = 0u;
+        __syncthreads();
+        if (tid == 0u) mi->hq_kb_n = 0u;
+      }
+    }
+    if (!STATEFUL) {
+      LACB_PH(8);
+      __syncthreads();
+      LACB_PH(9);
+      if (tid == 0u) mi->hq_kb_n = 0u;
+      return;
+    }
+  }
   uint32_t* K = sm.Kpl() + tid * (E / 4);
   if (STATEFUL) {
-    constexpr bool COOP = (NT >= 64) && (E == 16);  // several warps to share the hard chunks between
-    AMisc* mi = sm.Misc();
-    sm.Flg()[tid] = flg;
-    if (COOP && tid == 0u) mi->hq_n = 0u;
-    LACB_PH(6);
-    __syncthreads();
-    LACB_PH(7);
+    constexpr bool COOP = COOPK;
+    if (!COOPK) {
+      sm.Flg()[tid] = flg;
+      LACB_PH(6);
+      __syncthreads();
+      LACB_PH(7);
+    }
     const bool done = k_bias_thread<NT, E, !COOP>(sm, pr, flg, kpk);
 #pragma unroll
     for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];  // biased k, or the base k of a chunk left for the pairs
@@ -980,7 +1081,7 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     Fz[ASmem<NT, E>::FBS + tid] = 0ull;
     Fz[2u * ASmem<NT, E>::FBS + tid] = 0ull;
   }
-  k_series<NT, E, STATEFUL>(sm, pr, n, sg);  // ends with a barrier
+  k_series<NT, E, STATEFUL>(sm, pr, n, sg, STATEFUL ? 0u : p);  // ends with a barrier
   uint32_t kinitA, kinitB = 0u;
   if (STATEFUL) {
     kinitA = mi->k_init;  // published by the last warp before the barriers inside k_series
