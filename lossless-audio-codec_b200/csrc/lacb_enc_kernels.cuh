@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         }
       }
       const uint32_t has_run = cost_pass<NT, E, true>(sm, pr, n, 0u, 0u);
-      if (tid == 0u) {
+      if (tid == (uint32_t)(NT - 32)) {  // bookkeeping on the last warp: the first warps are the loaded ones
         const u64 stat = mi->stat_bits;
         const uint32_t k_init = mi->k_init, k_stat = mi->k_stat;
         const u64 rice = mi->tot_rice, bin = mi->tot_bin;
