@@ -15,7 +15,7 @@ dll.lacb_debug_phase_clk(buf, 1)
 v = np.array(buf[:], dtype=np.float64)
 tot = v[:64].sum()
 names = {0: "load_block", 1: "residual(+loop top)", 2: "prepare->scan", 3: "wait scan", 4: "prepare rest", 5: "wait any4",
-         6: "static k + kbase/flags", 7: "wait flg", 8: "bias / k store", 9: "wait K", 10: "walk+reduce", 11: "wait totals",
+         6: "base k + flags (1-warp builds)", 7: "wait flg", 8: "base k, flags, bias, pairs", 9: "wait K / queues", 10: "walk+reduce", 11: "wait totals",
          12: "seg tables", 13: "wait seg", 14: "level scans", 15: "wait level", 16: "level select", 17: "final size", 18: "final sum"}
 print("analyze_ms", cd.timing()["analyze_ms"])
 for base, tag in ((0, "candidates"), (20, "levels/final")):
@@ -24,4 +24,6 @@ for base, tag in ((0, "candidates"), (20, "levels/final")):
             print(f"{tag:13s} {i:2d} {names.get(i, ''):24s} {100 * v[base + i] / tot:6.2f}%")
 for i, nm in enumerate(("kbase/flags", "bias", "walk")):
     w = v[64 + 32 * i: 96 + 32 * i]
+    if not w.any():
+        continue
     print(f"busy per warp, {nm}: " + " ".join(f"{x / w.mean():.2f}" for x in w))
