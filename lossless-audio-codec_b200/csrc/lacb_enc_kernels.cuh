@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
     int32_t r[E];
     compute_residual<NT, E>(x, g0, n, type, order, rec->taps, rec->coef, r);
     Prep<NT, E> pr;
-    prepare<NT, E, false>(sm, r, n, pr);  // U plane, prefix of u, last-nonzero scan (plane totals unused)
+    prepare<NT, E, false, true>(sm, r, n, pr);  // U plane, prefix of u, last-nonzero scan, run flag
     // segment tables of the chosen level
     for (uint32_t s = tid; s < nparts; s += NT) {
       const uint32_t sid = nparts - 1u + s;

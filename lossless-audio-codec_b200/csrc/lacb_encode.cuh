@@ -316,7 +316,9 @@ __device__ __forceinline__ void load_u(const ASmem<NT, E>& sm, uint32_t (&u)[E])
 template <int NT, int E>
 __device__ __forceinline__ uint32_t zero_lookahead(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n);
 
-template <int NT, int E, bool FULL>
+// LIGHT (the emitter): only what the token walk needs -- U plane, prefix of u, last-non-zero scan, run flag;
+// no bit-plane counts and no lower bound.
+template <int NT, int E, bool FULL, bool LIGHT = false>
 __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&r)[E], uint32_t n, Prep<NT, E>& pr) {
   const uint32_t tid = threadIdx.x, g0 = tid * E;
   AMisc* mi = sm.Misc();
@@ -331,7 +333,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     u[j] = uu;
     S += uu;
     uor |= uu;
-    if (!FULL) {
+    if (!FULL && !LIGHT) {
       clzsum += (uint32_t)__clz((int)uu);
       n4 += uu == 4u ? 1u : 0u;
     }
@@ -347,7 +349,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   // zero run can be free; zero-run escapes and tags only add.  Candidates whose bound already
   // exceeds the best exact cost so far are dropped before the expensive adaptive-k passes.
   uint32_t lbt = 0u;
-  if (!FULL) {
+  if (!FULL && !LIGHT) {
     const uint32_t inr = g0 >= n ? 0u : (n - g0 < (uint32_t)E ? n - g0 : (uint32_t)E);
     lbt = 33u * (uint32_t)E - clzsum;                                // sum of bit_width(u) + 1, zeros counted as 1
     lbt -= (uint32_t)__popc(zmask) + ((uint32_t)E - inr) + n4;       // zeros and missing samples: 0; u == 4: 3
@@ -360,13 +362,13 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
 #pragma unroll
   for (int c = 0; c < E / 4; ++c)
     U4[swz_chunk(tid * (E / 4) + c)] = make_uint4(u[4 * c], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
-  if (!FULL && tid < 8) {
+  if (!FULL && !LIGHT && tid < 8) {
     mi->cnt_tot[tid] = 0u;
     mi->cnt_first[tid] = 0u;
     if (tid == 0) mi->lb = 0u;
   }
-  uint32_t V[5];
-  csa_count<E>(u, V);
+  uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
+  if (!LIGHT) csa_count<E>(u, V);
   // one pass: prefix of u and index of the last non-zero residual before the chunk.  Its
   // barrier also orders the U plane and the zeroed counters before everything below.
   u64 total;
@@ -380,8 +382,10 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   if (NT * E > 256 && g0 == 256u) mi->p_first = pr.Pex;
 
   PlaneCounts pc;
-  planes_from_sliced(V, pc);
-  if (FULL) {
+  if (!LIGHT) planes_from_sliced(V, pc);
+  if (LIGHT) {
+    // nothing to count
+  } else if (FULL) {
     PlaneCounts* Cp = sm.Cpre();
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
