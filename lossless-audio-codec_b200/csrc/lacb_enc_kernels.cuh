@@ -410,19 +410,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         __syncthreads();  // everyone has read lb / best before the next candidate resets them
         continue;
       }
-      // initial / static k of the whole block from the block totals, one k per lane.  Only thread 0
-      // consumes them (two barriers later), so the last warp -- on average the least loaded one, the
-      // first warps carry the block start where k moves most -- evaluates them for everybody.
-      if ((tid >> 5) == (uint32_t)(NT / 32 - 1)) {
-        u64 sb;
-        const uint32_t ki = warp_best_static_k(mi->p_first, mi->cnt_first, n < 256u ? n : 256u, 12, nullptr);
-        const uint32_t ks = warp_best_static_k(mi->u_total, mi->cnt_tot, n, 15, &sb);
-        if ((tid & 31u) == 0u) {
-          mi->k_init = ki;
-          mi->k_stat = ks;
-          mi->stat_bits = sb;
-        }
-      }
+      // (the block's initial / static k are evaluated inside the pass, see block_static_k)
       const uint32_t has_run = cost_pass<NT, E, true>(sm, pr, n, 0u, 0u);
       if (tid == (uint32_t)(NT - 32)) {  // bookkeeping on the last warp: the first warps are the loaded ones
         const u64 stat = mi->stat_bits;

@@ -847,7 +847,24 @@ __device__ __forceinline__ void k_bias_pair(const ASmem<NT, E>& sm, uint32_t tA,
   if (live) Kb[g0 + j] = (uint8_t)k;
 }
 
-template <int NT, int E, bool STATEFUL>
+// Initial / static k of the whole block from the block totals (one k per lane), for the candidate passes.
+// Only thread 0 (first sample of the walk) and the bookkeeping thread consume them, two barriers later.
+template <int NT, int E>
+__device__ __forceinline__ void block_static_k(const ASmem<NT, E>& sm, uint32_t n) {
+  AMisc* mi = sm.Misc();
+  u64 sb;
+  const uint32_t ki = warp_best_static_k(mi->p_first, mi->cnt_first, n < 256u ? n : 256u, 12, nullptr);
+  const uint32_t ks = warp_best_static_k(mi->u_total, mi->cnt_tot, n, 15, &sb);
+  if ((threadIdx.x & 31u) == 0u) {
+    mi->k_init = ki;
+    mi->k_stat = ks;
+    mi->stat_bits = sb;
+  }
+}
+
+// STATK: also evaluate block_static_k, on the last warp and in the interval where the other warps deal
+// with the queued chunks (it used to sit in front of the first barrier, where everybody waited for it).
+template <int NT, int E, bool STATEFUL, bool STATK = false>
 __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                          const SegGeom& sg, uint32_t p = 0u) {
   const uint32_t tid = threadIdx.x;
@@ -881,6 +898,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
     if (nh <= (uint32_t)NT / 8u) {
       for (uint32_t i = (tid >> 5) * 2u; i < nh; i += (uint32_t)(NT / 32) * 2u)
         k_base_pair<NT, E, STATEFUL>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu, n, p);
+      if (STATK && (tid >> 5) == (uint32_t)(NT / 32 - 1)) block_static_k<NT, E>(sm, n);
       if (STATEFUL) {
         if (have) sm.Flg()[tid] = flg;
         if (tid == 0u) mi->hq_n = 0u;
@@ -894,6 +912,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
         }
       }
     } else {
+      if (STATK && (tid >> 5) == (uint32_t)(NT / 32 - 1)) block_static_k<NT, E>(sm, n);
       if (!have) {
         k_series_thread<NT, E, STATEFUL, true, false>(sm, pr, n, sg, kpk, flg);
         if (!STATEFUL) {
@@ -921,6 +940,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
   if (STATEFUL) {
     constexpr bool COOP = COOPK;
     if (!COOPK) {
+      if (STATK && (tid >> 5) == (uint32_t)(NT / 32 - 1)) block_static_k<NT, E>(sm, n);
       sm.Flg()[tid] = flg;
       LACB_PH(6);
       __syncthreads();
@@ -1085,7 +1105,7 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     Fz[ASmem<NT, E>::FBS + tid] = 0ull;
     Fz[2u * ASmem<NT, E>::FBS + tid] = 0ull;
   }
-  k_series<NT, E, STATEFUL>(sm, pr, n, sg, STATEFUL ? 0u : p);  // ends with a barrier
+  k_series<NT, E, STATEFUL, STATEFUL>(sm, pr, n, sg, STATEFUL ? 0u : p);  // ends with a barrier
   uint32_t kinitA, kinitB = 0u;
   if (STATEFUL) {
     kinitA = mi->k_init;  // published by the last warp before the barriers inside k_series
