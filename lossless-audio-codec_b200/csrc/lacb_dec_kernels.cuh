@@ -294,7 +294,7 @@ struct Stage {
 };
 
 // Makes sure the 64 words from the one holding bit `pos` are in the ring: a batch of 32 tokens
-// spans at most 32 * 58 + 31 bits and every token is looked at through a 2-word window.
+// spans at most 32 * 59 + 31 bits and every token is looked at through a 2-word window.
 __device__ __forceinline__ void stage_ensure(const BitRd& r, ParseScratch* sc, Stage& sg, u64 pos, uint32_t lane) {
   const u64 wq = pos >> 5;
   const uint32_t wi = wq > 0xFFFFFF00ull ? 0xFFFFFF00u : (uint32_t)wq;
@@ -352,13 +352,20 @@ __device__ __forceinline__ uint32_t walk_tokens(const u64* ring, uint32_t* tp, u
                                                 uint32_t k, uint32_t B) {
   uint32_t cnt = 0u;
   if (mode == MODE_RICE || mode == MODE_STATIC) {
+    // No exit test on the chain: a unary run that does not end inside the 32-bit view counts as 32
+    // ones (clz(0) = 32) and the walk simply goes on; the lane that extracts the token sees q >= 32,
+    // flags it, and everything from there on is discarded and redone by the exact reader.
     const uint32_t k1 = k + 1u;
-#pragma unroll 4
+    for (; cnt + 4u <= B; cnt += 4u) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        tp[cnt + i] = rel;
+        rel += (uint32_t)__clz((int)~ring_peek(ring, rel)) + k1;
+      }
+    }
     for (; cnt < B; ++cnt) {
       tp[cnt] = rel;
-      const uint32_t hi = ring_peek(ring, rel);
-      if (hi == 0xFFFFFFFFu) break;
-      rel += (uint32_t)__clz((int)~hi) + k1;
+      rel += (uint32_t)__clz((int)~ring_peek(ring, rel)) + k1;
     }
   } else if (mode == MODE_ZR) {
     for (; cnt < B; ++cnt) {
@@ -431,7 +438,9 @@ __device__ __forceinline__ bool decode_segment_fast(BitRd& r, u64& pos, uint32_t
       w = 1u;
       if (mode == MODE_RICE || mode == MODE_STATIC) {
         const uint32_t rem = k ? ring_peek(sc->ring, e - k) >> (32u - k) : 0u;
-        u = ((e - s - 1u - k) << k) | rem;
+        const uint32_t q = e - s - 1u - k;
+        bad = bad || q >= 32u;  // the walker could not see the end of the unary run
+        u = (q << k) | rem;
       } else {
         const uint32_t hs = ring_peek(sc->ring, s);
         const uint32_t tag = hs >> 30;
