@@ -97,25 +97,6 @@ __device__ __forceinline__ uint32_t swz(uint32_t i) { return (swz_chunk(i >> 2) 
 // ---------------------------------------------------------------------------
 // Adaptive Rice parameter, division-free closed forms.
 //
-// Stateless model (block/encoder.cpp:72-77): mean = (sum + (count>>1)) / count,
-// k = mean <= 1 ? 0 : min(31, bit_width(mean-1)).  With N = sum + (count>>1):
-//   bit_width(floor(N/c) - 1) = min{ w >= 1 : N < ((1<<w) + 1) * c }.
-// `hint` is a guess for the answer (e.g. the previous sample's k): the search walks
-// from it, so a good hint costs two comparisons.
-__device__ __forceinline__ uint32_t kbase_from(u64 N, uint32_t c, uint32_t hint) {
-  if (N < 2ull * c) return 0u;  // mean <= 1
-  // smallest w in [1,32] with N < (c << w) + c ; N < 2^47, c < 2^15 so no overflow up to w = 48
-  uint32_t w = hint < 1u ? 1u : (hint > 33u ? 33u : hint);
-  while (w > 1u && N < (((u64)c) << (w - 1u)) + c) --w;   // (w-1) also satisfies -> go down
-  while (w < 33u && !(N < (((u64)c) << w) + c)) ++w;      // w does not satisfy -> go up
-  return w > 31u ? 31u : w;
-}
-__device__ __forceinline__ uint32_t kbase_guess(u64 N, uint32_t c) {
-  // floor(log2(N)) - floor(log2(c)) is within +-1 of the answer
-  const int g = (int)bitwidth64(N) - (int)(32 - __clz((int)c));
-  return g < 1 ? 1u : (uint32_t)g;
-}
-
 // Exact base k of the adaptive models without a division or a search:
 //   mean = floor(N / c), k = mean <= 1 ? 0 : min(31, bit_width(mean - 1))
 // With M = N - c >= c:  bit_width(mean - 1) = 1 + max{ s : (M >> s) >= c }, and that s is
@@ -202,34 +183,6 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* sc
   __syncthreads();
   if (total) *total = tot;
   return (w ? wprev : 0u) + inc - v;
-}
-
-// exclusive running maximum of a signed value (identity = -1)
-template <int NT>
-__device__ __forceinline__ int32_t block_excl_max_i32(int32_t v, int32_t* scratch) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
-  constexpr int NW = (NT + 31) / 32;
-  int32_t inc = v;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int32_t y = __shfl_up_sync(kFull, inc, d);
-    if (lane >= (uint32_t)d && y > inc) inc = y;
-  }
-  int32_t ex = __shfl_up_sync(kFull, inc, 1);
-  if (lane == 0u) ex = -1;
-  if (NW == 1) return ex;
-  if (lane == 31u) scratch[w] = inc;
-  __syncthreads();
-  int32_t ws = (lane < (uint32_t)NW) ? scratch[lane] : -1;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int32_t y = __shfl_up_sync(kFull, ws, d);
-    if (lane >= (uint32_t)d && y > ws) ws = y;
-  }
-  const int32_t wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
-  __syncthreads();
-  if (w && wprev > ex) ex = wprev;
-  return ex;
 }
 
 // Exclusive sum scan and exclusive running maximum (identity -1) of one value pair per thread

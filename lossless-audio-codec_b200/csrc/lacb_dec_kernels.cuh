@@ -3,14 +3,16 @@
 // The .lac block bitstream is inherently serial inside a block: variable-length
 // codes whose Rice parameter adapts to every decoded value, and no byte offsets for
 // partitions or for the second channel (docs/format.md:18-27).  The
-// only parallelism the format offers is the block count, so:
-//   k_parse_blocks   one warp per frame-block; lane 0 walks the bitstream with a
-//                    64-bit peek window (3 cached word loads + 2 funnel shifts per
-//                    symbol, no refill state), the closed-form division-free k model
-//                    and a 256-entry shared-memory ring for the drift window.  A
-//                    divergent thread-per-block layout was measured 40x slower.
+// only independent units are the blocks, so:
+//   k_parse_blocks   one warp per frame-block.  Partitioned (stateless-k) and static segments
+//                    are decoded in speculative batches: lane 0 only places up to 32 token
+//                    boundaries from a shared-memory ring of the bitstream assuming k stays
+//                    put, the 32 lanes extract the tokens, recompute k with one prefix scan
+//                    and commit the prefix that used the right k; anything unusual goes to the
+//                    exact serial reader.  Unpartitioned adaptive segments (stateful model)
+//                    use the serial reader throughout.
 //   k_restore_blocks one thread per channel-block: fixed / FIR / LPC reconstruction,
-//                    counted loops without data-dependent trip counts.
+//                    chunks staged through shared memory with cp.async.
 //   k_finish_pcm     mid/side reconstruction, PCM range validation, interleave +
 //                    16/24-bit packing; fully data parallel and bandwidth bound.
 // Reference: Block::Decoder::decode_into src/codec/block/decoder.cpp:64-520,

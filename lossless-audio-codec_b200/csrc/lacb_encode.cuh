@@ -73,7 +73,7 @@ struct AMisc {
   BestCand best;
   u64 tot_rice, tot_zr, tot_bin, u_total, p_first, stat_bits, red64;
   uint32_t cnt_tot[8], cnt_first[8];
-  uint32_t k_init, k_stat, has_run, red32;
+  uint32_t k_init, k_stat;  // initial / static k of the candidate (block_static_k)
   uint32_t lb;  // lower bound of the candidate's cost (see prepare)
   uint32_t hq_n, hq_kb_n;  // entries in the hard-chunk queue (bias pairs / base-k pairs)
   uint32_t hasrun_bits[8];
@@ -862,113 +862,108 @@ __device__ __forceinline__ void block_static_k(const ASmem<NT, E>& sm, uint32_t 
   }
 }
 
-// STATK: also evaluate block_static_k, on the last warp and in the interval where the other warps deal
-// with the queued chunks (it used to sit in front of the first barrier, where everybody waited for it).
+// Appends this thread's chunk to the block-wide queue of chunks that need per-sample work
+// (one shared-memory atomic per warp).  Warp collective.
+template <int NT, int E>
+__device__ __forceinline__ void queue_push(const ASmem<NT, E>& sm, uint32_t* counter, bool want) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t m = __ballot_sync(kFull, want);
+  if (!m) return;
+  uint32_t base = 0u;
+  if (lane == 0u) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(kFull, base, 0);
+  if (want) sm.HardQ()[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+}
+
+// The k series of one level, left in the K plane (ends with a barrier).
+//
+// Stage 1, base k: one evaluation per chunk where k provably stays put (k_series_thread); the
+// chunks where it moves are queued block-wide and dealt to all warps in pairs, one lane per sample
+// (k_base_pair) -- unless most chunks are like that (short segments of the deep partition levels),
+// in which case every owner runs the per-sample loop itself, the cheaper form then.
+// Stage 2, stateful model only: bias by chunk-level proofs (k_bias_thread), the chunks that need
+// the per-sample recurrences again queued and evaluated in pairs (k_bias_pair).
+// Single-warp builds (the 256-sample probes) have nobody to share with and keep the per-thread loops.
+//
+// STATK: the last warp also evaluates block_static_k, in the interval where the other warps work
+// on the queued chunks.
 template <int NT, int E, bool STATEFUL, bool STATK = false>
 __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                          const SegGeom& sg, uint32_t p = 0u) {
-  const uint32_t tid = threadIdx.x;
-  constexpr bool COOPK = (NT >= 64) && (E == 16);  // several warps to share the hard chunks between
+  constexpr bool COOP = (NT >= 64) && (E == 16);
+  constexpr uint32_t NW = NT / 32;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5;
   AMisc* mi = sm.Misc();
+  uint32_t* K = sm.Kpl() + tid * (E / 4);
+  const uint16_t* hq = sm.HardQ();
   uint32_t kpk[E / 4];
   uint32_t flg;
+  auto store_k = [&]() {
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];
+  };
+
+  // ---- stage 1: base k (+ flag word)
   bool have;
-  if (sg.fast) have = k_series_thread<NT, E, STATEFUL, true, COOPK>(sm, pr, n, sg, kpk, flg);
+  if (sg.fast) have = k_series_thread<NT, E, STATEFUL, true, COOP>(sm, pr, n, sg, kpk, flg);
   else have = k_series_thread<NT, E, STATEFUL, false, false>(sm, pr, n, sg, kpk, flg);
-  if constexpr (COOPK) {
-    // chunks whose k moves inside them: queued block-wide and dealt to the warps in pairs (k_base_pair);
-    // when most chunks are like that (short segments of the deep partition levels) every owner runs the
-    // per-sample loop itself, which is the cheaper form then
-    uint16_t* hq = sm.HardQ();
-    const uint32_t lane = tid & 31u;
-    const uint32_t hm = __ballot_sync(kFull, !have);
-    if (hm) {
-      uint32_t base = 0u;
-      if (lane == 0u) base = atomicAdd(&mi->hq_kb_n, (uint32_t)__popc(hm));
-      base = __shfl_sync(kFull, base, 0);
-      if (!have) hq[base + (uint32_t)__popc(hm & ((1u << lane) - 1u))] = (uint16_t)tid;
-    }
-    if (have && !STATEFUL) {
-      uint32_t* K0 = sm.Kpl() + tid * (E / 4);
-#pragma unroll
-      for (int c4 = 0; c4 < E / 4; ++c4) K0[c4] = kpk[c4];
-    }
-    __syncthreads();
+  if constexpr (COOP) {
+    queue_push<NT, E>(sm, &mi->hq_kb_n, !have);
+    if (have && !STATEFUL) store_k();
+    __syncthreads();  // queue complete
     const uint32_t nh = mi->hq_kb_n;
-    if (nh <= (uint32_t)NT / 8u) {
-      for (uint32_t i = (tid >> 5) * 2u; i < nh; i += (uint32_t)(NT / 32) * 2u)
+    const bool pairs = nh <= (uint32_t)NT / 8u;
+    if (pairs) {
+      for (uint32_t i = warp * 2u; i < nh; i += NW * 2u)
         k_base_pair<NT, E, STATEFUL>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu, n, p);
-      if (STATK && (tid >> 5) == (uint32_t)(NT / 32 - 1)) block_static_k<NT, E>(sm, n);
-      if (STATEFUL) {
-        if (have) sm.Flg()[tid] = flg;
-        if (tid == 0u) mi->hq_n = 0u;
-        __syncthreads();
-        if (tid == 0u) mi->hq_kb_n = 0u;  // consumed; the next pushes are at least one barrier away
-        if (!have) {  // pick up what the pairs produced for this chunk
-          const uint32_t* K0 = sm.Kpl() + tid * (E / 4);
-#pragma unroll
-          for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = K0[c4];
-          flg = sm.Flg()[tid];
-        }
-      }
-    } else {
-      if (STATK && (tid >> 5) == (uint32_t)(NT / 32 - 1)) block_static_k<NT, E>(sm, n);
-      if (!have) {
-        k_series_thread<NT, E, STATEFUL, true, false>(sm, pr, n, sg, kpk, flg);
-        if (!STATEFUL) {
-          uint32_t* K0 = sm.Kpl() + tid * (E / 4);
-#pragma unroll
-          for (int c4 = 0; c4 < E / 4; ++c4) K0[c4] = kpk[c4];
-        }
-      }
-      if (STATEFUL) {
-        sm.Flg()[tid] = flg;
-        if (tid == 0u) mi->hq_n = 0u;
-        __syncthreads();
-        if (tid == 0u) mi->hq_kb_n = 0u;
-      }
+    } else if (!have) {
+      k_series_thread<NT, E, STATEFUL, true, false>(sm, pr, n, sg, kpk, flg);
+      if (!STATEFUL) store_k();
+      have = true;
     }
+    if (STATK && warp == NW - 1u) block_static_k<NT, E>(sm, n);
     if (!STATEFUL) {
       LACB_PH(8);
       __syncthreads();
       LACB_PH(9);
-      if (tid == 0u) mi->hq_kb_n = 0u;
+      if (tid == 0u) mi->hq_kb_n = 0u;  // consumed; the next pushes are at least one barrier away
       return;
     }
-  }
-  uint32_t* K = sm.Kpl() + tid * (E / 4);
-  if (STATEFUL) {
-    constexpr bool COOP = COOPK;
-    if (!COOPK) {
-      if (STATK && (tid >> 5) == (uint32_t)(NT / 32 - 1)) block_static_k<NT, E>(sm, n);
-      sm.Flg()[tid] = flg;
-      LACB_PH(6);
-      __syncthreads();
-      LACB_PH(7);
-    }
-    const bool done = k_bias_thread<NT, E, !COOP>(sm, pr, flg, kpk);
+    if (have) sm.Flg()[tid] = flg;
+    if (tid == 0u) mi->hq_n = 0u;
+    __syncthreads();  // flag words (and the k bytes of the queued chunks) complete
+    if (tid == 0u) mi->hq_kb_n = 0u;
+    if (!have) {  // pick up what the pairs produced for this chunk
 #pragma unroll
-    for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];  // biased k, or the base k of a chunk left for the pairs
-    if constexpr (COOP) {
-      uint16_t* hq = sm.HardQ();
-      const uint32_t lane = tid & 31u;
-      const uint32_t hm = __ballot_sync(kFull, !done);
-      if (hm) {  // one shared-memory atomic per warp
-        uint32_t base = 0u;
-        if (lane == 0u) base = atomicAdd(&mi->hq_n, (uint32_t)__popc(hm));
-        base = __shfl_sync(kFull, base, 0);
-        if (!done) hq[base + (uint32_t)__popc(hm & ((1u << lane) - 1u))] = (uint16_t)tid;
-      }
+      for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = K[c4];
+      flg = sm.Flg()[tid];
+    }
+  } else {
+    if (!STATEFUL) {
+      store_k();
       LACB_PH(8);
       __syncthreads();
       LACB_PH(9);
-      const uint32_t nh = mi->hq_n;
-      for (uint32_t i = (tid >> 5) * 2u; i < nh; i += (uint32_t)(NT / 32) * 2u)
-        k_bias_pair<NT, E>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu);
+      return;
     }
-  } else {
-#pragma unroll
-    for (int c4 = 0; c4 < E / 4; ++c4) K[c4] = kpk[c4];
+    if (STATK && warp == NW - 1u) block_static_k<NT, E>(sm, n);
+    sm.Flg()[tid] = flg;
+    LACB_PH(6);
+    __syncthreads();
+    LACB_PH(7);
+  }
+
+  // ---- stage 2 (stateful model): bias
+  const bool done = k_bias_thread<NT, E, !COOP>(sm, pr, flg, kpk);
+  store_k();  // biased k, or the base k of a chunk left for the pairs
+  if constexpr (COOP) {
+    queue_push<NT, E>(sm, &mi->hq_n, !done);
+    LACB_PH(8);
+    __syncthreads();
+    LACB_PH(9);
+    const uint32_t nh = mi->hq_n;
+    for (uint32_t i = warp * 2u; i < nh; i += NW * 2u)
+      k_bias_pair<NT, E>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu);
   }
   LACB_PH(8);
   __syncthreads();
