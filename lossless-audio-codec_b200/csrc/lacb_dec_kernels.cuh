@@ -463,7 +463,20 @@ __device__ __forceinline__ bool decode_segment_fast(BitRd& r, u64& pos, uint32_t
     uint32_t PW = w;
     u64 PU = u;
     uint32_t knext = k;
-    if (adaptive) {
+    if (mode == MODE_RICE && k <= 21u) {
+      // plain adaptive Rice: one sample per token, and every token of the batch is below
+      // 32 << k <= 2^26 (larger ones are flagged bad), so the prefix of u fits 32 bits
+      uint32_t p32 = bad ? 0u : u;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, p32, d);
+        if (lane >= (uint32_t)d) p32 += y;
+      }
+      PU = p32;
+      PW = lane + 1u;
+      const uint32_t c = count + PW;
+      knext = kbase_clz(sum + PU + (c >> 1), c);
+    } else if (adaptive) {
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const u64 yu = __shfl_up_sync(kFull, PU, d);
@@ -718,31 +731,60 @@ __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* st
   return true;
 }
 
+// Fixed predictor of order 1..4 (block/decoder.cpp:308-352).  Only wrapping 32-bit arithmetic sits on the
+// sample-to-sample chain (one to three instructions); the int32 range verdict is the same sum in 64 bits,
+// which nothing later depends on.  The 32-bit value is exact as long as no sample has failed, and a failing
+// sample ends the block.
+template <int ORDER>
+__device__ __forceinline__ bool restore_fixed(int32_t* x, uint32_t n, int4* stage, uint32_t stride) {
+  int32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+  return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
+    uint32_t p;
+    i64 p64;
+    if (ORDER == 1) {
+      p = (uint32_t)h1;
+      p64 = h1;
+    } else if (ORDER == 2) {
+      p = 2u * (uint32_t)h1 - (uint32_t)h2;
+      p64 = 2 * (i64)h1 - h2;
+    } else if (ORDER == 3) {
+      p = 3u * (uint32_t)h1 - 3u * (uint32_t)h2 + (uint32_t)h3;
+      p64 = 3 * (i64)h1 - 3 * (i64)h2 + h3;
+    } else {
+      p = 4u * (uint32_t)h1 - 6u * (uint32_t)h2 + 4u * (uint32_t)h3 - (uint32_t)h4;
+      p64 = 4 * (i64)h1 - 6 * (i64)h2 + 4 * (i64)h3 - h4;
+    }
+    const bool pred = i >= (uint32_t)ORDER;  // the first ORDER samples are verbatim
+    const int32_t s32 = (int32_t)((uint32_t)val + (pred ? p : 0u));
+    const i64 s64 = (i64)val + (pred ? p64 : 0ll);
+    val = s32;
+    h4 = h3; h3 = h2; h2 = h1; h1 = s32;
+    return s64 == (i64)s32;  // a failing sample ends the block at the end of its chunk
+  });
+}
+
 // restore_*_in_place, block/decoder.cpp:308-403: every reconstructed sample must fit int32
 __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t type, uint32_t order, const int16_t* c,
                                               int4* stage, uint32_t stride) {
   if (type == PRED_FIXED) {
-    if (order == 0u) return true;
-    i64 h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-    return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
-      i64 p;
-      if (order == 1u) p = h1;
-      else if (order == 2u) p = 2 * h1 - h2;
-      else if (order == 3u) p = 3 * h1 - 3 * h2 + h3;
-      else p = 4 * h1 - 6 * h2 + 4 * h3 - h4;
-      const i64 s = (i64)val + (i >= order ? p : 0ll);  // the first `order` samples are verbatim
-      val = (int32_t)s;
-      h4 = h3; h3 = h2; h2 = h1; h1 = s;
-      return s == (i64)(int32_t)s;  // a failing sample ends the block at the end of its chunk
-    });
+    switch (order) {
+      case 0: return true;
+      case 1: return restore_fixed<1>(x, n, stage, stride);
+      case 2: return restore_fixed<2>(x, n, stage, stride);
+      case 3: return restore_fixed<3>(x, n, stage, stride);
+      default: return restore_fixed<4>(x, n, stage, stride);
+    }
   }
   if (type == PRED_FIR) {
-    i64 h1 = 0, h2 = 0;
+    int32_t h1 = 0, h2 = 0;
     return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
-      const i64 s = (i64)val + (i >= 2u ? ((3 * h1 - h2) >> 2) : 0ll);
-      val = (int32_t)s;
-      h2 = h1; h1 = s;
-      return s == (i64)(int32_t)s;
+      const i64 t = (3 * (i64)h1 - h2) >> 2;
+      const bool pred = i >= 2u;
+      const int32_t s32 = (int32_t)((uint32_t)val + (pred ? (uint32_t)t : 0u));
+      const i64 s64 = (i64)val + (pred ? t : 0ll);
+      val = s32;
+      h2 = h1; h1 = s32;
+      return s64 == (i64)s32;
     });
   }
   if (order <= 12u) {
@@ -765,12 +807,15 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
         if (t + 2 <= 12) a2 = mad_wide(cf[t + 2], h[t + 2], a2);
       }
       const i64 acc = mad_wide(cf[1], h[1], a0 + a1 + a2);
-      const i64 s = (acc >> 15) + (i64)val;
-      val = (int32_t)s;
+      // on the chain: the multiply-add, one funnel shift for the low word of acc >> 15, one 32-bit add;
+      // the range verdict uses the 64-bit sum, which nothing later depends on
+      const int32_t s32 = (int32_t)((uint32_t)val + (uint32_t)(acc >> 15));
+      const i64 s64 = (acc >> 15) + (i64)val;
+      val = s32;
 #pragma unroll
       for (int t = 12; t >= 2; --t) h[t] = h[t - 1];
-      h[1] = (int32_t)s;
-      return s == (i64)(int32_t)s;
+      h[1] = s32;
+      return s64 == (i64)s32;
     });
   }
   for (uint32_t i = 0; i < n; ++i) {  // orders 13..32: legal in the format, never produced by the encoder

@@ -96,6 +96,11 @@ def test_block_decoder_fuzz_all_modes(cd):
     assert fuzz_block_decoder(cd, 7, names, 8) > 20
 
 
+def test_restore_overflow_verdicts(cd):
+    from test_gpu_parity import restore_overflow_fuzz
+    assert restore_overflow_fuzz(cd, 8, 10) > 40
+
+
 def test_sliced_host_pipeline():
     from test_gpu_parity import run_sliced
     run_sliced("emu_codec", 3)

@@ -294,3 +294,40 @@ def test_repeatability(cd):
         a, b, _ = cd.decode(want2)
         assert np.array_equal(a, dl) and np.array_equal(b, dr)
     assert np.array_equal(dl, l2) and np.array_equal(dr, r2)
+
+
+def restore_overflow_fuzz(cd, rounds, flips):
+    """Signals near int32 full scale whose predictors leave small residuals: a flipped residual bit makes the
+    reconstruction leave int32, which Block::Decoder rejects (block/decoder.cpp:308-403).  The restore kernel
+    keeps only 32-bit arithmetic on its sample-to-sample chain, so its 64-bit verdict is checked here."""
+    rng = np.random.default_rng(3)
+    rejected = 0
+    for it in range(rounds):
+        n = int(rng.choice([512, 2048, 4096]))
+        t = np.arange(n)
+        kind = it % 4
+        if kind == 0:
+            x = (2**31 - 2000 - 3 * t).astype(np.int64)
+        elif kind == 1:
+            x = (-(2**31) + 5000 + (t * t) // 50).astype(np.int64)
+        elif kind == 2:
+            x = np.round((2**31 - 10) * np.sin(2 * np.pi * t / 97.0)).astype(np.int64)
+        else:
+            x = np.round((2**31 - 10) * np.sin(2 * np.pi * t / 31.0) * np.cos(2 * np.pi * t / 411.0)).astype(np.int64)
+        pcm = np.clip(x + rng.integers(-3, 4, n), -(2**31), 2**31 - 1).astype(np.int32)
+        good = H.oracle().block_encode(pcm, 1, 1)
+        assert cd.block_encode(pcm, 1, 1) == good
+        for _ in range(flips):
+            b = bytearray(good)
+            b[int(rng.integers(3, len(b)))] ^= 1 << int(rng.integers(0, 8))
+            ok_a, dec_a, bits_a = H.oracle().block_decode(bytes(b), n)
+            ok_b, dec_b, bits_b = cd.block_decode(bytes(b), n)
+            assert ok_a == ok_b, (it, kind)
+            rejected += not ok_a
+            if ok_a:
+                assert bits_a == bits_b and np.array_equal(dec_a, dec_b)
+    return rejected
+
+
+def test_restore_overflow_verdicts(cd):
+    assert restore_overflow_fuzz(cd, 24, 25) > 300
