@@ -671,16 +671,24 @@ __device__ __forceinline__ void cp_async_wait() {
 
 constexpr int kRestoreDepth = 6;  // chunks of 8 samples in flight per thread
 
-// Runs step(i, value&) over x[0..n) in order, 8 samples at a time.  One thread owns the whole
-// serial recurrence, so memory latency of the in-place pattern (load x[i] -> compute -> store
-// x[i]) can only be hidden by distance: chunk c + kRestoreDepth is requested (cp.async into
-// the thread's own staging slots, `stage` with `stride` int4 between slots) when chunk c is
-// taken out.  Chunks move as 128-bit vectors when the plane is 16-byte aligned (every block
-// start of a regular stream is).
-template <typename Step>
-__device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* stage, uint32_t stride, Step&& step) {
+// Runs the recurrence over x[0..n) in order, 8 samples at a time.  One thread owns the whole
+// serial chain, so
+//  * memory latency of the in-place pattern (load x[i] -> compute -> store x[i]) is hidden by
+//    distance: chunk c + kRestoreDepth is requested (cp.async into the thread's own staging
+//    slots, `stage` with `stride` int4 between slots) when chunk c is taken out;
+//  * the chain itself is kept to what the next sample needs: step(i, value&, aux&) produces the
+//    sample in wrapping 32-bit arithmetic, and the int32 range verdicts of the reference are
+//    computed afterwards for the whole chunk by verify(i, residual, sample, aux, h1..h4) -- eight
+//    mutually independent checks instead of a check inside every link of the chain.  The 32-bit
+//    samples are exact as long as no sample has failed, and a failing sample ends the block.
+// Chunks move as 128-bit vectors when the plane is 16-byte aligned (every block start of a
+// regular stream is).
+template <typename Step, typename Verify>
+__device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* stage, uint32_t stride, Step&& step,
+                                                Verify&& verify) {
   constexpr int D = kRestoreDepth;
   const bool aligned = (reinterpret_cast<uint64_t>(x) & 15ull) == 0ull;
+  int32_t t1 = 0, t2 = 0, t3 = 0, t4 = 0;  // the four samples before the current chunk
   uint32_t i = 0;
   if (aligned) {
     const uint32_t nch = n >> 3;
@@ -705,18 +713,27 @@ __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* st
             cp_async16(stage + (2 * d + 1) * stride, x4 + 2 * (c + D) + 1);
           }
           cp_async_commit();
-          int32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-          // no branch per sample: the verdicts are collected and looked at once per chunk, so the
-          // scheduler can overlap the independent parts of neighbouring samples
+          const int32_t in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          int32_t v[12];  // v[0..3] = the four samples before the chunk (oldest first), v[4..11] = the chunk
+          v[0] = t4; v[1] = t3; v[2] = t2; v[3] = t1;
+          i64 aux[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 + j] = in[j];
+            aux[j] = 0;
+            step(c * 8u + (uint32_t)j, v[4 + j], aux[j]);
+          }
           bool ok = true;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ok = step(c * 8u + (uint32_t)j, v[j]) && ok;
+          for (int j = 0; j < 8; ++j)
+            ok = verify(c * 8u + (uint32_t)j, in[j], v[4 + j], aux[j], v[3 + j], v[2 + j], v[1 + j], v[j]) && ok;
           if (!ok) {
             cp_async_wait<0>();
             return false;
           }
-          x4[2 * c] = make_int4(v[0], v[1], v[2], v[3]);
-          x4[2 * c + 1] = make_int4(v[4], v[5], v[6], v[7]);
+          x4[2 * c] = make_int4(v[4], v[5], v[6], v[7]);
+          x4[2 * c + 1] = make_int4(v[8], v[9], v[10], v[11]);
+          t4 = v[8]; t3 = v[9]; t2 = v[10]; t1 = v[11];
         }
       }
     }
@@ -724,43 +741,42 @@ __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* st
     i = nch << 3;
   }
   for (; i < n; ++i) {
-    int32_t t = x[i];
-    if (!step(i, t)) return false;
+    const int32_t in = x[i];
+    int32_t t = in;
+    i64 aux = 0;
+    step(i, t, aux);
+    if (!verify(i, in, t, aux, t1, t2, t3, t4)) return false;
     x[i] = t;
+    t4 = t3; t3 = t2; t2 = t1; t1 = t;
   }
   return true;
 }
 
-// Fixed predictor of order 1..4 (block/decoder.cpp:308-352).  Only wrapping 32-bit arithmetic sits on the
-// sample-to-sample chain (one to three instructions); the int32 range verdict is the same sum in 64 bits,
-// which nothing later depends on.  The 32-bit value is exact as long as no sample has failed, and a failing
-// sample ends the block.
+// Fixed predictor of order 1..4 (block/decoder.cpp:308-352): one to three wrapping 32-bit instructions
+// per link of the chain; the verdict repeats the sum in 64 bits from the finished samples.
 template <int ORDER>
 __device__ __forceinline__ bool restore_fixed(int32_t* x, uint32_t n, int4* stage, uint32_t stride) {
-  int32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-  return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
-    uint32_t p;
-    i64 p64;
-    if (ORDER == 1) {
-      p = (uint32_t)h1;
-      p64 = h1;
-    } else if (ORDER == 2) {
-      p = 2u * (uint32_t)h1 - (uint32_t)h2;
-      p64 = 2 * (i64)h1 - h2;
-    } else if (ORDER == 3) {
-      p = 3u * (uint32_t)h1 - 3u * (uint32_t)h2 + (uint32_t)h3;
-      p64 = 3 * (i64)h1 - 3 * (i64)h2 + h3;
-    } else {
-      p = 4u * (uint32_t)h1 - 6u * (uint32_t)h2 + 4u * (uint32_t)h3 - (uint32_t)h4;
-      p64 = 4 * (i64)h1 - 6 * (i64)h2 + 4 * (i64)h3 - h4;
-    }
-    const bool pred = i >= (uint32_t)ORDER;  // the first ORDER samples are verbatim
-    const int32_t s32 = (int32_t)((uint32_t)val + (pred ? p : 0u));
-    const i64 s64 = (i64)val + (pred ? p64 : 0ll);
-    val = s32;
-    h4 = h3; h3 = h2; h2 = h1; h1 = s32;
-    return s64 == (i64)s32;  // a failing sample ends the block at the end of its chunk
-  });
+  uint32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+  return restore_chunked(
+      x, n, stage, stride,
+      [&](uint32_t i, int32_t& val, i64&) {
+        uint32_t p;
+        if (ORDER == 1) p = h1;
+        else if (ORDER == 2) p = 2u * h1 - h2;
+        else if (ORDER == 3) p = 3u * h1 - 3u * h2 + h3;
+        else p = 4u * h1 - 6u * h2 + 4u * h3 - h4;
+        const uint32_t s = (uint32_t)val + (i >= (uint32_t)ORDER ? p : 0u);  // the first ORDER samples are verbatim
+        val = (int32_t)s;
+        h4 = h3; h3 = h2; h2 = h1; h1 = s;
+      },
+      [](uint32_t i, int32_t in, int32_t out, i64, int32_t g1, int32_t g2, int32_t g3, int32_t g4) {
+        i64 p;
+        if (ORDER == 1) p = g1;
+        else if (ORDER == 2) p = 2 * (i64)g1 - g2;
+        else if (ORDER == 3) p = 3 * (i64)g1 - 3 * (i64)g2 + g3;
+        else p = 4 * (i64)g1 - 6 * (i64)g2 + 4 * (i64)g3 - g4;
+        return i < (uint32_t)ORDER || (i64)in + p == (i64)out;
+      });
 }
 
 // restore_*_in_place, block/decoder.cpp:308-403: every reconstructed sample must fit int32
@@ -777,15 +793,16 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
   }
   if (type == PRED_FIR) {
     int32_t h1 = 0, h2 = 0;
-    return restore_chunked(x, n, stage, stride, [&](uint32_t i, int32_t& val) {
-      const i64 t = (3 * (i64)h1 - h2) >> 2;
-      const bool pred = i >= 2u;
-      const int32_t s32 = (int32_t)((uint32_t)val + (pred ? (uint32_t)t : 0u));
-      const i64 s64 = (i64)val + (pred ? t : 0ll);
-      val = s32;
-      h2 = h1; h1 = s32;
-      return s64 == (i64)s32;
-    });
+    return restore_chunked(
+        x, n, stage, stride,
+        [&](uint32_t i, int32_t& val, i64&) {
+          const uint32_t t = (uint32_t)((3 * (i64)h1 - h2) >> 2);
+          val = (int32_t)((uint32_t)val + (i >= 2u ? t : 0u));
+          h2 = h1; h1 = val;
+        },
+        [](uint32_t i, int32_t in, int32_t out, i64, int32_t g1, int32_t g2, int32_t, int32_t) {
+          return i < 2u || (i64)in + ((3 * (i64)g1 - g2) >> 2) == (i64)out;
+        });
   }
   if (order <= 12u) {
     // history before the block start is zero, which reproduces taps = min(order, i)
@@ -795,28 +812,27 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
     int32_t h[13];
 #pragma unroll
     for (int t = 0; t <= 12; ++t) h[t] = 0;
-    return restore_chunked(x, n, stage, stride, [&](uint32_t, int32_t& val) {
-      // taps 2..12 do not depend on the previous sample: only c1*h1 sits on the serial chain
-      // three independent partial sums: a single chain of twelve dependent multiply-adds would
-      // be longer than the recurrence's own critical path (c1 * h1 -> shift -> add -> check)
-      i64 a0 = 0, a1 = 0, a2 = 0;
+    return restore_chunked(
+        x, n, stage, stride,
+        [&](uint32_t, int32_t& val, i64& aux) {
+          // taps 2..12 do not depend on the previous sample: only c1*h1 sits on the serial chain, and three
+          // independent partial sums keep the other eleven multiply-adds off it
+          i64 a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
-      for (int t = 2; t <= 12; t += 3) {
-        a0 = mad_wide(cf[t], h[t], a0);
-        if (t + 1 <= 12) a1 = mad_wide(cf[t + 1], h[t + 1], a1);
-        if (t + 2 <= 12) a2 = mad_wide(cf[t + 2], h[t + 2], a2);
-      }
-      const i64 acc = mad_wide(cf[1], h[1], a0 + a1 + a2);
-      // on the chain: the multiply-add, one funnel shift for the low word of acc >> 15, one 32-bit add;
-      // the range verdict uses the 64-bit sum, which nothing later depends on
-      const int32_t s32 = (int32_t)((uint32_t)val + (uint32_t)(acc >> 15));
-      const i64 s64 = (acc >> 15) + (i64)val;
-      val = s32;
+          for (int t = 2; t <= 12; t += 3) {
+            a0 = mad_wide(cf[t], h[t], a0);
+            if (t + 1 <= 12) a1 = mad_wide(cf[t + 1], h[t + 1], a1);
+            if (t + 2 <= 12) a2 = mad_wide(cf[t + 2], h[t + 2], a2);
+          }
+          aux = mad_wide(cf[1], h[1], a0 + a1 + a2) >> 15;  // the prediction, kept in 64 bits for the verdict
+          val = (int32_t)((uint32_t)val + (uint32_t)aux);
 #pragma unroll
-      for (int t = 12; t >= 2; --t) h[t] = h[t - 1];
-      h[1] = s32;
-      return s64 == (i64)s32;
-    });
+          for (int t = 12; t >= 2; --t) h[t] = h[t - 1];
+          h[1] = val;
+        },
+        [](uint32_t, int32_t in, int32_t out, i64 aux, int32_t, int32_t, int32_t, int32_t) {
+          return aux + (i64)in == (i64)out;
+        });
   }
   for (uint32_t i = 0; i < n; ++i) {  // orders 13..32: legal in the format, never produced by the encoder
     i64 acc = 0;
