@@ -1,6 +1,8 @@
 """`lac_cli encode` / `lac_cli decode` wall times on the GPU box next to the unmodified reference CLI
 (oracle/_ref/lac_cli_ref) on the same files: BASELINE configs[0] (60 s 16/44.1 auto) and configs[1]
 (600 s 24/96 --stereo-mode=ms).  Writes one JSON line per config; files live in /dev/shm.
+Measurement tool (like bench.py's cpu_baseline leg): the reference CLI is only timed and compared, never used by
+the product.
 usage: cli_timing.py [out.jsonl]"""
 import json, os, struct, subprocess, sys, time
 sys.path.insert(0, "tests")
