@@ -257,6 +257,26 @@ for depth, mode, ch in ((16, 2, 2), (24, 1, 2), (24, 0, 1)):
     except RuntimeError as e:
         g, eg = None, str(e)
     assert ea == eg, (ea, eg)
+# incompressible input: the payload outgrows the library's first allocation in the sliced path (realloc),
+# and a caller buffer that is too small must be reported with the size it needs
+rng = np.random.default_rng(1)
+l = rng.integers(-32768, 32768, 12 * 16384 + 5).astype(np.int32)
+r = rng.integers(-32768, 32768, l.size).astype(np.int32)
+want = H.oracle().encode(l, r, 44100, 16, 0)
+assert len(want) > l.size * 4
+assert cd.encode(l, r, 44100, 16, 0) == want
+pk = np.empty(l.size * 4, dtype=np.uint8)
+iv = np.stack([l, r], axis=1).astype("<i2").view(np.uint8).reshape(-1)
+small = np.zeros(l.size * 2, dtype=np.uint8)
+bb = np.zeros(13, dtype=np.uint32)
+try:
+    cd.encode_into(iv, small, bb, 16, 2, 0)
+    raise SystemExit("small buffer accepted")
+except RuntimeError as e:
+    need = int(str(e).split("needs ")[1].split(" ")[0])
+big = np.zeros(need, dtype=np.uint8)
+n = cd.encode_into(iv, big, bb, 16, 2, 0)
+assert n == need and int(bb.sum()) == n
 print("sliced ok")
 """
 
