@@ -853,7 +853,8 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));
   auto kf = k_finish_pcm;
   LACB_LAUNCH(kf, lacb_umin(n_blocks, (uint32_t)ctx->sms * 8u), 256, 0, st, cfg, as<u64>(ctx->d_fs),
-              as<uint32_t>(ctx->d_size), dL, dR, as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms), d_packed);
+              as<uint32_t>(ctx->d_size), dL, dR, as<uint32_t>(ctx->d_err), as<uint8_t>(ctx->d_ms), d_packed,
+              (uint32_t)(dL != as<int32_t>(ctx->d_L)) /* caller-owned planes are part of the result */);
   CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
   return 0;
 }

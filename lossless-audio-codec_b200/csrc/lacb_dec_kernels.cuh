@@ -1021,19 +1021,23 @@ __global__ void k_merge_restore_errors(DecCfg cfg, uint32_t* blk_err) {
 __global__ void __launch_bounds__(256) k_finish_pcm(DecCfg cfg, const u64* __restrict__ blk_fs,
                                                     const uint32_t* __restrict__ blk_size, int32_t* L, int32_t* R,
                                                     uint32_t* blk_err, const uint8_t* __restrict__ blk_ms,
-                                                    uint8_t* out_packed) {
+                                                    uint8_t* out_packed, uint32_t keep_planes) {
   const int32_t lo = cfg.bit_depth == 16u ? -32768 : -8388608, hi = cfg.bit_depth == 16u ? 32767 : 8388607;
-  const uint32_t bps = cfg.bit_depth / 8u;
+  const uint32_t bps = cfg.bit_depth / 8u, ch = cfg.channels;
+  const uint32_t mask = cfg.bit_depth == 16u ? 0xFFFFu : 0xFFFFFFu;
+  // the planes only have to be fixed up when somebody reads them afterwards
+  const bool planes = keep_planes != 0u || out_packed == nullptr;
   for (uint32_t b = blockIdx.x; b < cfg.n_blocks; b += gridDim.x) {
     const uint32_t e = blk_err[b];
     if (e != DERR_OK && e != DERR_TRAILING) continue;  // samples are garbage
     const u64 fs = blk_fs[b];
     const uint32_t n = blk_size[b];
-    const bool ms = cfg.channels == 2u && blk_ms[b];
+    const bool ms = ch == 2u && blk_ms[b];
     uint32_t bad = 0u;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    // one frame: mid/side -> left/right (lac/decoder.cpp:48-65), depth check, stores
+    auto frame = [&](uint32_t i) {
       i64 l = L[fs + i], r = 0;
-      if (cfg.channels == 2u) {
+      if (ch == 2u) {
         r = R[fs + i];
         if (ms) {
           const i64 m = l, sd = r;
@@ -1041,21 +1045,72 @@ __global__ void __launch_bounds__(256) k_finish_pcm(DecCfg cfg, const u64* __res
           r = l - sd;
         }
       }
-      const bool ok = l >= lo && l <= hi && (cfg.channels == 1u || (r >= lo && r <= hi));
+      const bool ok = l >= lo && l <= hi && (ch == 1u || (r >= lo && r <= hi));
       bad |= !ok;
-      if (ok) {
+      if (!ok) return;
+      if (ms && planes) {
+        L[fs + i] = (int32_t)l;
+        R[fs + i] = (int32_t)r;
+      }
+      if (out_packed) {
+        uint8_t* o = out_packed + (fs + i) * (u64)(bps * ch);
+        for (uint32_t k = 0; k < bps; ++k) o[k] = (uint8_t)((uint32_t)(int32_t)l >> (8u * k));
+        if (ch == 2u)
+          for (uint32_t k = 0; k < bps; ++k) o[bps + k] = (uint8_t)((uint32_t)(int32_t)r >> (8u * k));
+      }
+    };
+    // four frames per thread with 128-bit plane accesses and whole-word packed stores when the block
+    // starts on a multiple of four frames (every block of a regular stream does)
+    const bool vec = (fs & 3ull) == 0ull && (reinterpret_cast<uint64_t>(L) & 15ull) == 0ull &&
+                     (ch == 1u || (reinterpret_cast<uint64_t>(R) & 15ull) == 0ull) &&
+                     (reinterpret_cast<uint64_t>(out_packed) & 3ull) == 0ull;
+    const uint32_t n4 = vec ? n >> 2 : 0u;
+    for (uint32_t q = threadIdx.x; q < n4; q += blockDim.x) {
+      int4* L4 = reinterpret_cast<int4*>(L + fs) + q;
+      int4* R4 = reinterpret_cast<int4*>(R + fs) + q;
+      const int4 a = *L4;
+      const int4 c = ch == 2u ? *R4 : make_int4(0, 0, 0, 0);
+      i64 l[4] = {a.x, a.y, a.z, a.w}, r[4] = {c.x, c.y, c.z, c.w};
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
         if (ms) {
-          L[fs + i] = (int32_t)l;
-          R[fs + i] = (int32_t)r;
+          const i64 m = l[k], sd = r[k];
+          l[k] = m + ((sd + (sd & 1)) >> 1);
+          r[k] = l[k] - sd;
         }
-        if (out_packed) {
-          uint8_t* o = out_packed + (fs + i) * (u64)(bps * cfg.channels);
-          for (uint32_t k = 0; k < bps; ++k) o[k] = (uint8_t)((uint32_t)(int32_t)l >> (8u * k));
-          if (cfg.channels == 2u)
-            for (uint32_t k = 0; k < bps; ++k) o[bps + k] = (uint8_t)((uint32_t)(int32_t)r >> (8u * k));
+        ok = ok && l[k] >= lo && l[k] <= hi && (ch == 1u || (r[k] >= lo && r[k] <= hi));
+      }
+      if (!ok) {  // rare: let the per-frame path decide which frames stand
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) frame(4u * q + k);
+        continue;
+      }
+      if (ms && planes) {
+        *L4 = make_int4((int32_t)l[0], (int32_t)l[1], (int32_t)l[2], (int32_t)l[3]);
+        *R4 = make_int4((int32_t)r[0], (int32_t)r[1], (int32_t)r[2], (int32_t)r[3]);
+      }
+      if (out_packed) {
+        uint32_t v[8];  // the samples of the four frames in stream order, masked to the sample width
+        uint32_t nv = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[nv++] = (uint32_t)(int32_t)l[k] & mask;
+          if (ch == 2u) v[nv++] = (uint32_t)(int32_t)r[k] & mask;
+        }
+        uint32_t* o = reinterpret_cast<uint32_t*>(out_packed + (fs + 4ull * q) * (u64)(bps * ch));
+        if (bps == 2u) {
+          for (uint32_t k = 0; k < nv; k += 2u) o[k >> 1] = v[k] | (v[k + 1u] << 16);
+        } else {  // 24-bit: four samples fill three words
+          for (uint32_t k = 0, w = 0; k < nv; k += 4u, w += 3u) {
+            o[w] = v[k] | (v[k + 1u] << 24);
+            o[w + 1u] = (v[k + 1u] >> 8) | (v[k + 2u] << 16);
+            o[w + 2u] = (v[k + 2u] >> 16) | (v[k + 3u] << 8);
+          }
         }
       }
     }
+    for (uint32_t i = 4u * n4 + threadIdx.x; i < n; i += blockDim.x) frame(i);
     if (__syncthreads_or((int)bad) && threadIdx.x == 0) blk_err[b] = DERR_RANGE;
   }
 }
