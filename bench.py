@@ -81,13 +81,21 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self) -> dict:
+    def mark(self) -> int:
+        return len(self.lines)
+
+    def stop(self, first: int = 0, last: int | None = None) -> dict:
+        """Clocks / throttle reasons of the samples [first, last) (marks taken around the timed region); when
+        the region was shorter than one sampling period the samples just around it are used."""
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
+        last = len(self.lines) if last is None else last
+        if last <= first:
+            first, last = max(0, first - 1), min(len(self.lines), last + 2)
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        for ln in self.lines[first:last]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -243,6 +251,8 @@ def main():
                     stats["stages"]["dec_" + k] = stats["stages"].get("dec_" + k, 0.0) + v
         return nbytes, bb
 
+    sampler = ClockSampler(local_rank)  # started before the warm-up: nvidia-smi needs ~0.1 s to deliver its first line
+    sampler.start()
     for _ in range(args.warmup):
         step_device(False)
     # correctness of the very data being timed: round trip restores the PCM bit for bit
@@ -250,15 +260,14 @@ def main():
     assert np.array_equal(back, pk), "device round trip does not restore the PCM"
     del back
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    m0 = sampler.mark()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_device(True)
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(m0, sampler.mark())
 
     # end to end through the C ABI with HOST buffers: every step copies the PCM host->device,
     # the payload device->host, the payload host->device again and the PCM device->host

@@ -85,13 +85,50 @@ __global__ void __launch_bounds__(1024) k_build_jobs(EncCfg cfg, const uint32_t*
 }
 
 // ---------------------------------------------------------------------------
-// K1: packed little-endian interleaved PCM -> int32 planes.  Each thread converts 4
-// frames; the packed bytes are read as aligned 32-bit words.
+// K1: packed little-endian interleaved PCM -> int32 planes.  A thread converts four frames: their
+// packed bytes are a whole number of aligned 32-bit words (8, 12, 16 or 24 bytes), the planes are
+// written with 128-bit stores; the frames behind the last full group of four are done one by one.
+__device__ __forceinline__ int32_t sext_sample(uint32_t v, uint32_t bps) {
+  return bps == 2u ? (int32_t)(int16_t)v : ((int32_t)(v << 8)) >> 8;
+}
 __global__ void k_deinterleave(const uint8_t* __restrict__ in, u64 frames, uint32_t channels, uint32_t bps,
                                int32_t* __restrict__ L, int32_t* __restrict__ R) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   const uint32_t fb = channels * bps;  // bytes per frame
-  for (u64 f = (u64)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += stride) {
+  const bool vec = (reinterpret_cast<uint64_t>(in) & 3ull) == 0ull && (reinterpret_cast<uint64_t>(L) & 15ull) == 0ull &&
+                   (channels == 1u || (reinterpret_cast<uint64_t>(R) & 15ull) == 0ull);
+  const u64 groups = vec ? frames >> 2 : 0ull;
+  const uint32_t mask = bps == 2u ? 0xFFFFu : 0xFFFFFFu;
+  for (u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(in + g * 4ull * fb);
+    uint32_t v[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};  // the samples of the four frames in stream order
+    const uint32_t ns = 4u * channels;
+    if (bps == 2u) {
+      for (uint32_t k = 0; k < ns; k += 2u) {
+        const uint32_t x = w[k >> 1];
+        v[k] = x & mask;
+        v[k + 1u] = x >> 16;
+      }
+    } else {  // 24-bit: three words hold four samples
+      for (uint32_t k = 0, i = 0; k < ns; k += 4u, i += 3u) {
+        const uint32_t a = w[i], b = w[i + 1u], c = w[i + 2u];
+        v[k] = a & mask;
+        v[k + 1u] = ((a >> 24) | (b << 8)) & mask;
+        v[k + 2u] = ((b >> 16) | (c << 16)) & mask;
+        v[k + 3u] = c >> 8;
+      }
+    }
+    if (channels == 2u) {
+      reinterpret_cast<int4*>(L)[g] = make_int4(sext_sample(v[0], bps), sext_sample(v[2], bps), sext_sample(v[4], bps),
+                                                sext_sample(v[6], bps));
+      reinterpret_cast<int4*>(R)[g] = make_int4(sext_sample(v[1], bps), sext_sample(v[3], bps), sext_sample(v[5], bps),
+                                                sext_sample(v[7], bps));
+    } else {
+      reinterpret_cast<int4*>(L)[g] = make_int4(sext_sample(v[0], bps), sext_sample(v[1], bps), sext_sample(v[2], bps),
+                                                sext_sample(v[3], bps));
+    }
+  }
+  for (u64 f = groups * 4ull + (u64)blockIdx.x * blockDim.x + threadIdx.x; f < frames; f += stride) {
     const uint8_t* p = in + f * fb;
     for (uint32_t c = 0; c < channels; ++c) {
       int32_t v;
