@@ -40,6 +40,28 @@ METRIC = "encode+decode PCM throughput (BASELINE: encode & decode PCM GB/s, byte
 UNIT = "GB/s"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout must carry the one JSON line and nothing else, but libraries write to it too (NCCL prints its
+    version banner there at communicator creation): everything else that goes to fd 1 is sent to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(obj) -> None:
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def synth_packed(seed: int, frames: int) -> np.ndarray:
     """SURVEY.md Appendix C generator (tools/lac_synth.c), packed 24-bit stereo bytes."""
     so = ROOT / "tools" / "liblac_synth.so"
@@ -147,7 +169,7 @@ def run_reference(args, rank):
         td += b
     val = pk.size * args.steps / (te + td) / 1e9
     sample = f"first {secs} s of the workload ({pk.size / 1e6:.1f} MB PCM), encode+decode, {cores} threads"
-    print(json.dumps({
+    emit_line({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64", "data": "synthetic",
@@ -155,7 +177,7 @@ def run_reference(args, rank):
         "encode_gbs": pk.size * args.steps / te / 1e9, "decode_gbs": pk.size * args.steps / td / 1e9,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_config(args, secs):
@@ -177,6 +199,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-contexts", type=int, default=1, help="contexts (host threads) the e2e leg splits the blocks over")
     args = ap.parse_args()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,8 +214,6 @@ def main():
         import torch
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner off stdout (the JSON line is the last line either way)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -389,7 +410,7 @@ def main():
             line["cpu_baseline"] = {"value": sb / (te + td) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                     "encode_gbs": sb / te / 1e9, "decode_gbs": sb / td / 1e9,
                                     "sample": f"first {secs} s of the workload ({sb / 1e6:.1f} MB PCM), best of 2"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     cd.dev_free(d_pcm)
     cd.dev_free(d_out)
     if dist:

@@ -17,8 +17,7 @@ from run_configs import synth_packed
 rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 secs = int(sys.argv[1]) if len(sys.argv) > 1 else 4500
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keeps NCCL's banner off stdout
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 cd = load_package().Codec(local)
