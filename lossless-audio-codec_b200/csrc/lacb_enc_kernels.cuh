@@ -777,10 +777,16 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
                             bool emit;
                             const Token t = make_token(m >> 5, m & 31u, u, k, is_zero, closes, long_run, &emit);
                             if (!emit) return;
-                            or_field(stg, W, pos, t.head, t.hlen);
-                            or_ones(stg, W, pos + t.hlen, t.q);
-                            or_field(stg, W, pos + t.hlen + t.q, t.tail, t.tlen);
-                            pos += (i64)t.hlen + t.q + t.tlen;
+                            const uint32_t tot = t.hlen + t.q + t.tlen;
+                            if (tot <= 32u) {  // the usual case: tag, unary run and tail go out as one field
+                              const u64 v = ((u64)t.head << (t.q + t.tlen)) | ((((u64)1 << t.q) - 1ull) << t.tlen) | t.tail;
+                              or_field(stg, W, pos, (uint32_t)v, tot);
+                            } else {
+                              or_field(stg, W, pos, t.head, t.hlen);
+                              or_ones(stg, W, pos + t.hlen, t.q);
+                              or_field(stg, W, pos + t.hlen + t.q, t.tail, t.tlen);
+                            }
+                            pos += (i64)tot;
                           });
       }
       __syncthreads();
