@@ -90,7 +90,7 @@ int lacb_get_timing(const lacb_ctx* ctx, lacb_timing* out);
  *                   LACB_PACKED_LE  -> pcm_a = interleaved bytes, pcm_b unused
  *   payload_out   : malloc'ed concatenation of all block payloads (lacb_free)
  *   block_bytes   : caller array of ceil(frames/16384) entries, compressed bytes per block
- * Long inputs are processed as slices of whole blocks on two internal streams, so that the
+ * Long inputs are processed as slices of whole blocks on internal streams, so that the
  * host<->device copies overlap the kernels; the bytes are those of a single pass.
  */
 int lacb_encode(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a, const void* pcm_b,

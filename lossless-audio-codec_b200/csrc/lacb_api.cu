@@ -459,16 +459,22 @@ int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
 }
 
 // ---------------------------------------------------------------------------
-// Pipelined host paths.  A long input is cut into slices of whole blocks; two slice contexts
-// (own stream, own workspace) alternate, so the host->device copy of slice i+1 and the
-// device->host copy of slice i-1 run under the kernels of slice i.  Blocks are independent, so
-// the bytes are those of a single pass.  A slice holds a multiple of the SM count of
-// channel-block jobs: the persistent analysis grid then ends on a full wave.
+// Pipelined host paths.  A long input is cut into slices of whole blocks that run on slice contexts
+// (own stream, own workspace), so the host->device copy of one slice and the device->host copy of
+// another run under the kernels of a third.  Blocks are independent, so the bytes are those of a
+// single pass.  The encoder alternates between two contexts and sizes its slices as a multiple of
+// the SM count of channel-block jobs (the persistent analysis grid then ends on a full wave); the
+// decoder keeps dec_kids() slices in flight (see lacb_decode).
 static uint32_t slice_blocks(const lacb_ctx* ctx, uint32_t channels) {
   static const long forced = getenv("LACB_SLICE_BLOCKS") ? atol(getenv("LACB_SLICE_BLOCKS")) : 0;  // tests / tuning
   if (forced > 0) return (uint32_t)forced;
   const uint32_t per_wave = ((uint32_t)ctx->sms + channels - 1u) / channels;  // blocks per wave of jobs
   return per_wave * 14u;
+}
+// slice contexts the host-buffer decode keeps in flight
+static uint32_t dec_kids() {
+  static const long forced = getenv("LACB_DEC_KIDS") ? atol(getenv("LACB_DEC_KIDS")) : 0;  // tuning
+  return forced >= 2 && forced <= 16 ? (uint32_t)forced : 4u;
 }
 static double trace_now() {
   struct timespec ts;
@@ -487,8 +493,8 @@ static bool trace_on() {
       fprintf(stderr, "\n");                         \
     }                                                \
   } while (0)
-static int ensure_kids(lacb_ctx* ctx) {
-  while (ctx->kids.size() < 2) {
+static int ensure_kids(lacb_ctx* ctx, size_t count = 2) {
+  while (ctx->kids.size() < count) {
     lacb_ctx* k = nullptr;
     const int rc = lacb_create(ctx->device, &k);
     if (rc != 0) {
@@ -540,8 +546,15 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
                               uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes, lacb_err* err) {
   CKR(ensure_kids(ctx));
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
+  // Slice plan: the first slices are short (2, 4, 8 waves of jobs) so that the kernels start after a
+  // fraction of a millisecond of copying and every later copy hides under the slice before it.
   const uint32_t sb = slice_blocks(ctx, prm->channels);
-  const uint32_t ns = (nb + sb - 1u) / sb;
+  std::vector<uint32_t> cut{0u};  // cut[i] = first block of slice i, cut[ns] = nb
+  if (getenv("LACB_SLICE_BLOCKS") == nullptr)
+    for (uint32_t w = 2u; w < 14u && cut.back() + sb / 14u * w + sb < nb; w *= 2u) cut.push_back(cut.back() + sb / 14u * w);
+  while (cut.back() + sb < nb) cut.push_back(cut.back() + sb);
+  cut.push_back(nb);
+  const uint32_t ns = (uint32_t)cut.size() - 1u;
   uint8_t* host = dst;
   uint64_t cap = dst_cap;
   if (!dst) {  // library-owned result: start from the raw size, grow if a stream expands
@@ -550,7 +563,7 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
     if (!host) return LACB_ENOMEM;
   }
   auto slice_range = [&](uint32_t i, uint64_t* f0, uint64_t* fr) {
-    const uint64_t b0 = (uint64_t)i * sb, b1 = b0 + sb < nb ? b0 + sb : nb;
+    const uint64_t b0 = cut[i], b1 = cut[i + 1u];
     *f0 = b0 * kMaxBlock;
     const uint64_t f1 = b1 * kMaxBlock < frames ? b1 * kMaxBlock : frames;
     *fr = f1 - *f0;
@@ -612,7 +625,7 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
     if (bb_stage)
       CKK(k, [&]() -> int {
         lacb_ctx* ctx = k;
-        CK(cudaMemcpyAsync(bb_stage + (size_t)i * sb, ctx->blk_bytes.p, (size_t)nbs * 4, cudaMemcpyDeviceToHost,
+        CK(cudaMemcpyAsync(bb_stage + cut[i], ctx->blk_bytes.p, (size_t)nbs * 4, cudaMemcpyDeviceToHost,
                            ctx->stream));
         return 0;
       }());
@@ -962,12 +975,19 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
   }
   const uint32_t bps = prm->bit_depth / 8;
   // The parser (one warp per block) and the restore kernel (one thread per channel-block) are serial
-  // chains: below ~32 blocks per SM a launch takes as long as a single block, so cutting a decode
-  // into slices only pays for very long inputs (measured: 3516 blocks decode faster in one piece).
-  const uint32_t dec_sb = getenv("LACB_SLICE_BLOCKS") ? slice_blocks(ctx, prm->channels) : (uint32_t)ctx->sms * 32u;
-  if (block_bytes && n_blocks >= 2u * dec_sb) {
+  // chains: a launch of a few hundred blocks takes as long as one of a few thousand (measured: 2.9 ms
+  // of parsing for 586 blocks, 3.55 ms for 3516), so slices cannot shorten the kernels.  What they
+  // buy is the copies: with four slices in flight on four streams the host->device copy of the
+  // payload and the device->host copy of the samples run under the chains of the other slices
+  // (14.9 -> 12.4 ms for 600 s of 24/96 stereo; more streams than that start to share hardware queues).
+  const uint32_t nk = dec_kids();
+  const uint32_t dec_sb = getenv("LACB_DEC_SLICE_BLOCKS") ? (uint32_t)atol(getenv("LACB_DEC_SLICE_BLOCKS"))
+                          : getenv("LACB_SLICE_BLOCKS")   ? slice_blocks(ctx, prm->channels)
+                          : n_blocks < 1024u              ? n_blocks
+                                                          : lacb_umin((uint32_t)ctx->sms * 32u, (n_blocks + nk - 1u) / nk);
+  if (block_bytes && dec_sb > 0u && n_blocks > dec_sb) {
     // pipelined: slices of whole blocks alternate between two slice contexts (see encode_host_sliced)
-    CKR(ensure_kids(ctx));
+    CKR(ensure_kids(ctx, nk));
     const uint32_t sb = dec_sb;
     const uint32_t ns = (n_blocks + sb - 1u) / sb;
     u64 tot_bytes = 0;
@@ -978,9 +998,8 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
       return LACB_EDECODE;
     }
     u64 boff = 0, foff = 0;
-    u64 s_b0[2] = {0, 0};
     auto begin = [&](uint32_t i) -> int {
-      lacb_ctx* k = ctx->kids[i & 1u];
+      lacb_ctx* k = ctx->kids[i % nk];
       const uint32_t b0 = i * sb, b1 = b0 + sb < n_blocks ? b0 + sb : n_blocks;
       u64 sbytes = 0, sframes = 0;
       for (uint32_t b = b0; b < b1; ++b) {
@@ -992,6 +1011,7 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
       CKR(ensure(ctx, ctx->d_L, sframes * 4));
       if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, sframes * 4));
       if (layout == LACB_PACKED_LE) CKR(ensure(ctx, ctx->d_packed, sframes * prm->channels * bps));
+      CK(cudaEventRecord(ctx->ev[EV_START], ctx->stream));
       CK(cudaMemcpyAsync(ctx->d_payload.p, payload + boff, sbytes, cudaMemcpyHostToDevice, ctx->stream));
       CKR(decode_common(ctx, prm, as<uint8_t>(ctx->d_payload), sbytes, block_sizes + b0, block_bytes + b0, b1 - b0,
                         as<int32_t>(ctx->d_L), as<int32_t>(ctx->d_R),
@@ -1006,28 +1026,39 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
           CK(cudaMemcpyAsync(static_cast<int32_t*>(out_b) + foff, ctx->d_R.p, sframes * 4, cudaMemcpyDeviceToHost,
                              ctx->stream));
       }
-      s_b0[i & 1u] = b0;
+      CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
       boff += sbytes;
       foff += sframes;
       return 0;
     };
-    int rc = begin(0);
-    for (uint32_t i = 0; i < ns && rc == 0; ++i) {
-      if (i + 1u < ns) rc = begin(i + 1u);
-      if (rc != 0) {
-        ctx->err = ctx->kids[(i + 1u) & 1u]->err;
-        break;
-      }
-      lacb_ctx* k = ctx->kids[i & 1u];
+    // up to nk slices are in flight; a slice context is collected (in block order, so the first failing
+    // block is the one reported) right before it is needed again, and at the end
+    auto collect = [&](uint32_t i) -> int {
+      lacb_ctx* k = ctx->kids[i % nk];
       const uint32_t b0 = i * sb, b1 = b0 + sb < n_blocks ? b0 + sb : n_blocks;
-      TRACE("dec slice %u queued, waiting for slice %u", i + 1u, i);
-      rc = decode_check_errors(k, b1 - b0, err, false, b0);  // waits for slice i only
-      TRACE("dec slice %u done", i);
-      if (rc != 0) ctx->err = k->err;
+      const int r = decode_check_errors(k, b1 - b0, err, false, b0);  // waits for slice i only
+      if (trace_on() && r == 0) {  // device timeline of the slice, relative to the start of the call
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        const int evs[6] = {EV_START, EV_H2D, EV_LPC, EV_ANALYZE, EV_EMIT, EV_D2H};
+        for (int e = 0; e < 6; ++e) cudaEventElapsedTime(&t[e], ctx->ev[EV_START], k->ev[evs[e]]);
+        TRACE("dec slice %u done: start %.2f h2d %.2f parse %.2f restore %.2f finish %.2f d2h %.2f ms", i, t[0], t[1],
+              t[2], t[3], t[4], t[5]);
+      }
+      if (r != 0) ctx->err = k->err;
+      return r;
+    };
+    if (trace_on()) cudaEventRecord(ctx->ev[EV_START], ctx->stream);
+    int rc = 0;
+    uint32_t queued = 0, collected = 0;
+    for (; queued < ns && rc == 0; ++queued) {
+      if (queued >= nk) rc = collect(collected++);
+      if (rc != 0) break;
+      rc = begin(queued);
+      if (rc != 0) ctx->err = ctx->kids[queued % nk]->err;
+      TRACE("dec slice %u queued", queued);
     }
-    if (rc != 0 && ctx->err.empty()) ctx->err = ctx->kids[0]->err;
+    while (rc == 0 && collected < queued) rc = collect(collected++);
     cudaDeviceSynchronize();
-    (void)s_b0;
     memset(&ctx->timing, 0, sizeof ctx->timing);
     return rc;
   }
