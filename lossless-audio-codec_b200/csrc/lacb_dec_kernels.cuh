@@ -293,6 +293,10 @@ struct ParseScratch {
 // staged word range [lo, hi) of the ring (warp-uniform registers)
 struct Stage {
   uint32_t lo, hi;
+  // Words of the chunk [pend_at, pend_at + 32) as loaded (little-endian), requested at the previous
+  // refill: a refill consumes loads that were issued ~64 tokens earlier instead of waiting for its own.
+  // pend1 is lane 31's right-hand neighbour (first word behind the chunk).
+  uint32_t pend_at, pend, pend1;
 };
 
 // Makes sure the 64 words from the one holding bit `pos` are in the ring: a batch of 32 tokens
@@ -304,15 +308,28 @@ __device__ __forceinline__ void stage_ensure(const BitRd& r, ParseScratch* sc, S
   bool any = false;
   while (sg.hi < wi + 64u) {  // the slots overwritten hold words below wi - 32
     const uint32_t i = sg.hi + lane;
-    const uint32_t w0 = rd_word(r, i);
+    uint32_t raw0, raw1 = 0u;
+    if (sg.pend_at == sg.hi) {
+      raw0 = sg.pend;
+      raw1 = sg.pend1;
+    } else {
+      raw0 = rd_word_raw(r, i);
+      if (lane == 31u) raw1 = rd_word_raw(r, i + 1u);
+    }
+    const uint32_t w0 = __byte_perm(raw0, 0u, 0x0123);
     uint32_t w1 = __shfl_down_sync(kFull, w0, 1);
-    if (lane == 31u) w1 = rd_word(r, i + 1u);
+    if (lane == 31u) w1 = __byte_perm(raw1, 0u, 0x0123);
     sc->ring[i & 127u] = ((u64)w0 << 32) | w1;
     sg.hi += 32u;
     any = true;
   }
   if (sg.hi - sg.lo > 128u) sg.lo = sg.hi - 128u;
-  if (any) __syncwarp();
+  if (any) {
+    sg.pend_at = sg.hi;  // request the next chunk; nothing reads these registers before the next refill
+    sg.pend = rd_word_raw(r, sg.hi + lane);
+    sg.pend1 = lane == 31u ? rd_word_raw(r, sg.hi + 32u) : 0u;
+    __syncwarp();
+  }
 }
 // Ring bit positions: rp = ((word index & 127) << 5) + bit, allowed to run past 4096 (the slot
 // index wraps in the address).  32 bits starting at ring position rp:
@@ -607,7 +624,7 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
   table_pos = __shfl_sync(kFull, table_pos, 0);
   const uint32_t cnt = 1u << p;
   u64 pos = table_pos + 7ull * cnt;  // first token; kept identical in all lanes
-  Stage stg = {0xFFFFFFFFu, 0xFFFFFFFFu};
+  Stage stg = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFEu, 0u, 0u};
   uint32_t off = 0u;
   for (uint32_t i = 0; i < cnt; ++i) {
     uint32_t mk = 0u;
