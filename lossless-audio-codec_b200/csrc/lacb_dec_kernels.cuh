@@ -338,6 +338,17 @@ __device__ __forceinline__ uint32_t ring_peek(const u64* ring, uint32_t rp) {
   return __funnelshift_l((uint32_t)v, (uint32_t)(v >> 32), rp);
 }
 
+// position of the most significant set bit, 0xFFFFFFFF for 0 (PTX bfind.u32, SASS FLO.U32)
+__device__ __forceinline__ uint32_t bfind_u32(uint32_t x) {
+#ifdef LACB_EMU
+  return 31u - (uint32_t)__clz((int)x);
+#else
+  uint32_t f;
+  asm("bfind.u32 %0, %1;" : "=r"(f) : "r"(x));
+  return f;
+#endif
+}
+
 // One token by the exact serial reader (lane 0 only): value u, sample count w.
 //   MODE_RICE / MODE_STATIC: Rice(k)             block/decoder.cpp:126-136, 296-303
 //   MODE_ZR  : tag 00 Rice(k) | 01 run | 10 raw  block/decoder.cpp:138-257
@@ -374,17 +385,19 @@ __device__ __forceinline__ uint32_t walk_tokens(const u64* ring, uint32_t* tp, u
     // No exit test on the chain: a unary run that does not end inside the 32-bit view counts as 32
     // ones (clz(0) = 32) and the walk simply goes on; the lane that extracts the token sees q >= 32,
     // flags it, and everything from there on is discarded and redone by the exact reader.
-    const uint32_t k1 = k + 1u;
+    // clz(x) = 31 - bfind(x) with bfind(0) = 0xFFFFFFFF: written out so that the constant part joins
+    // k + 1 and one three-input add is left on the chain (ptxas keeps 31 - x as a separate add otherwise)
+    const uint32_t k32 = k + 32u;
     for (; cnt + 4u <= B; cnt += 4u) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         tp[cnt + i] = rel;
-        rel += (uint32_t)__clz((int)~ring_peek(ring, rel)) + k1;
+        rel = rel + k32 - bfind_u32(~ring_peek(ring, rel));
       }
     }
     for (; cnt < B; ++cnt) {
       tp[cnt] = rel;
-      rel += (uint32_t)__clz((int)~ring_peek(ring, rel)) + k1;
+      rel = rel + k32 - bfind_u32(~ring_peek(ring, rel));
     }
   } else if (mode == MODE_ZR) {
     for (; cnt < B; ++cnt) {
