@@ -141,7 +141,26 @@ def cpu_codec():
     return H.oracle(), "port"
 
 
-def cpu_roundtrip(codec, l, r, threads):
+def cpu_roundtrip(codec, kind, l, r, threads):
+    """One encode + decode of the planes on the host cores -> (encode s, decode s, .lac bytes).  With the compiled
+    reference the clock runs inside the shim around LAC::Encoder::encode / LAC::Decoder::decode only (the
+    std::vector copies a C caller needs are made before it starts, oracle/ref_shim.cpp); the decode is checked
+    against the input there."""
+    import helpers as H
+    lp, rp = l.ctypes.data_as(H.i32p), r.ctypes.data_as(H.i32p)
+    if kind == "reference":
+        L = codec.lib
+        L.ref_encode_timed.argtypes = [H.i32p, H.i32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.POINTER(H.u8p), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        L.ref_decode_timed.argtypes = [H.u8p, C.c_uint64, C.c_uint32, H.i32p, H.i32p, C.c_uint64,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        out, n, te, td, match = H.u8p(), C.c_uint64(), C.c_double(), C.c_double(), C.c_int()
+        rc = L.ref_encode_timed(lp, rp, l.size, RATE, DEPTH, STEREO_MODE, threads, C.byref(out), C.byref(n), C.byref(te))
+        assert rc == 0, codec.last_error()
+        rc = L.ref_decode_timed(out, n.value, threads, lp, rp, l.size, C.byref(td), C.byref(match))
+        codec.free(out)
+        assert rc == 0 and match.value == 1, "reference round trip does not restore the PCM"
+        return te.value, td.value, n.value
     t0 = time.perf_counter()
     blob = codec.encode(l, r, RATE, DEPTH, STEREO_MODE, threads=threads)
     t1 = time.perf_counter()
@@ -151,30 +170,39 @@ def cpu_roundtrip(codec, l, r, threads):
     return t1 - t0, t2 - t1, len(blob)
 
 
+def cpu_sample(args):
+    """The CPU legs run the SAME workload as the GPU arm (the whole `--seconds` of rank 0's input, ~3 s of work
+    per step on 16 threads); `--cpu-seconds` can bound it further, and the line then says so."""
+    import helpers as H
+    secs = args.seconds if args.cpu_seconds <= 0 else min(args.cpu_seconds, args.seconds)
+    l, r = H.synth(2, RATE * secs, DEPTH)
+    nbytes = l.size * CHANNELS * (DEPTH // 8)
+    what = (f"the whole workload ({secs} s, {nbytes / 1e6:.1f} MB PCM)" if secs == args.seconds
+            else f"first {secs} s of the workload ({nbytes / 1e6:.1f} MB PCM)")
+    return l, r, nbytes, secs, what
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     codec, kind = cpu_codec()
     cores = os.cpu_count() or 1
-    secs = args.cpu_seconds
-    frames = RATE * secs
-    pk = synth_packed(2, frames)
-    l, r = unpack24(pk)
+    l, r, nbytes, secs, what = cpu_sample(args)
     for _ in range(args.warmup):
-        cpu_roundtrip(codec, l, r, cores)
+        cpu_roundtrip(codec, kind, l, r, cores)
     te = td = 0.0
     for _ in range(args.steps):
-        a, b, _ = cpu_roundtrip(codec, l, r, cores)
+        a, b, _ = cpu_roundtrip(codec, kind, l, r, cores)
         te += a
         td += b
-    val = pk.size * args.steps / (te + td) / 1e9
-    sample = f"first {secs} s of the workload ({pk.size / 1e6:.1f} MB PCM), encode+decode, {cores} threads"
+    val = nbytes * args.steps / (te + td) / 1e9
+    sample = f"{what} per step, encode+decode, {cores} threads, timed around LAC::Encoder::encode / LAC::Decoder::decode"
     emit_line({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32/int64", "data": "synthetic",
-        "config": workload_config(args, args.seconds),  # the GPU arm's workload; each step times `sample` of it
-        "encode_gbs": pk.size * args.steps / te / 1e9, "decode_gbs": pk.size * args.steps / td / 1e9,
+        "config": workload_config(args, secs),  # the workload this run timed (== the GPU arm's unless --cpu-seconds bounds it)
+        "encode_gbs": nbytes * args.steps / te / 1e9, "decode_gbs": nbytes * args.steps / td / 1e9,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -188,6 +216,181 @@ def workload_config(args, secs):
             "parallelism": f"block-range sharding x{args.gpus}, NCCL all-gather of payload byte counts only"}
 
 
+def run_c4(args, cd, rank, world, dist, torch):
+    """BASELINE config 4 as specified: ONE 10 h 24-bit / 48 kHz stereo file (auto LR/MS), sharded by contiguous
+    block range over the `world` ranks (ceil(n_blocks / world) blocks each), through the host-buffer C ABI.
+
+    encode : every rank copies its PCM range host->device and encodes it, the ranks all-gather their payload byte
+             counts over NCCL, and every rank DMAs its slab from HBM to its GLOBAL offset inside the one mapped
+             output file and writes its table slice (rank 0 adds header + block count): src/codec/lac/encoder.cpp:445-465
+             done by `world` processes.  All of that is inside the timed region.
+    check  : every rank's slab and table slice against the reference's SHA-256 (tests/golden/golden_large.json,
+             recorded from the unmodified reference by tools/make_golden_large.py), rank 0 the assembled file.
+    decode : every rank decodes its slab back to packed PCM in host memory; compared with the input.
+    Returns the `c4` sub-record on rank 0."""
+    import hashlib
+    import helpers as H
+    g = json.loads((ROOT / "tests" / "golden" / "golden_large.json").read_text())["C4_full_10h_24_48k_auto"]
+    frames_total, nb_total, depth, ch, mode = g["frames"], g["n_blocks"], g["depth"], g["channels"], g["stereo_mode"]
+    shard = g["shards"][str(world)][rank]
+    b0, nbr = shard["first_block"], shard["blocks"]
+    f0 = b0 * 16384
+    fr = min(frames_total, (b0 + nbr) * 16384) - f0
+    fb = ch * (depth // 8)
+    t_gen = time.perf_counter()
+    h_in = cd.pinned(fr * fb)
+    H.synth_lib().lac_synth_range(g["seed"], f0, fr, depth, ch, g["reset_log2"], None, None,
+                                  h_in.ctypes.data_as(H.u8p))
+    t_gen = time.perf_counter() - t_gen
+    h_out = cd.pinned(fr * fb)
+    d_pcm = cd.dev_malloc(fr * fb)
+    sizes = np.full(nbr, 16384, dtype=np.uint32)
+    sizes[-1] = fr - 16384 * (nbr - 1)
+    shm = Path("/dev/shm")
+    try:
+        base = shm if shm.is_dir() and os.statvfs(shm).f_bavail * os.statvfs(shm).f_frsize > g["len"] + (1 << 30) else Path("/tmp")
+    except OSError:
+        base = Path("/tmp")
+    out_path = base / f"lacb_c4_{os.environ.get('MASTER_PORT', 'single')}.lac"
+    counts = torch.zeros(world, dtype=torch.int64, device="cuda") if dist else None
+    mine = torch.zeros(1, dtype=torch.int64, device="cuda") if dist else None
+
+    def barrier():
+        if dist:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if rank == 0:
+        with open(out_path, "wb") as f:
+            f.truncate(g["len"])
+    barrier()
+    # every rank maps the ONE output file; its slab is DMA-ed from HBM straight to its global offset in the
+    # mapping (page-locked with lacb_host_register once the offset is known), so the host "concatenation" is the
+    # device->host copy itself: no staging buffer, no memcpy
+    import mmap
+    fd = os.open(out_path, os.O_RDWR)
+    mm = mmap.mmap(fd, g["len"])
+    mm_arr = np.frombuffer(mm, dtype=np.uint8)
+    base_ptr = mm_arr.ctypes.data
+    state = {"registered": None, "bb": None, "off": 0}
+    res = {}
+
+    def encode_step():
+        cd.h2d(d_pcm, h_in)
+        d_payload, n, d_bb = cd.encode_device(d_pcm, 0, fr, depth, ch, mode)
+        bb = cd.d2h(d_bb, nbr * 4, np.uint32)
+        if dist:  # global slab offsets = exclusive scan of the gathered byte counts
+            mine[0] = n
+            dist.all_gather_into_tensor(counts, mine)
+            allc = counts.cpu().numpy()
+        else:
+            allc = np.array([n], dtype=np.int64)
+        t_a = time.perf_counter()
+        off = 14 + 8 * nb_total + int(allc[:rank].sum())
+        table = np.empty((nbr, 2), dtype=">u4")
+        table[:, 0] = sizes
+        table[:, 1] = bb
+        mm_arr[14 + 8 * b0:14 + 8 * (b0 + nbr)] = np.frombuffer(table.tobytes(), dtype=np.uint8)
+        if state["registered"] is None:
+            lo = (base_ptr + off) & ~4095
+            hi = (base_ptr + off + n + 4095) & ~4095
+            state["registered"] = (lo, hi - lo) if cd.host_register(lo, hi - lo) else False
+        cd.d2h_to(base_ptr + off, d_payload, n)
+        if rank == 0:
+            mm_arr[:14] = np.frombuffer(lacb_header(ch, mode, g["rate"], depth) + int(nb_total).to_bytes(4, "big"), dtype=np.uint8)
+        state["bb"], state["off"] = bb, off
+        return n, int(allc.sum()), time.perf_counter() - t_a
+
+    def decode_step(n):  # reads the slab back out of the assembled file
+        cd.decode_into(mm_arr[state["off"]:state["off"] + n], sizes, state["bb"], depth, ch, mode, h_out)
+
+    n, total, _ = encode_step()  # warm-up (workspaces grow here) + the verified pass
+    decode_step(n)
+    barrier()
+    ok_slab = n == shard["payload_bytes"] and hashlib.sha256(memoryview(mm_arr[state["off"]:state["off"] + n])).hexdigest() == shard["payload_sha256"]
+    tb = np.empty((nbr, 2), dtype=">u4")
+    tb[:, 0] = sizes
+    tb[:, 1] = state["bb"]
+    ok_table = hashlib.sha256(tb.tobytes()).hexdigest() == shard["table_sha256"]
+    ok_rt = bool(np.array_equal(h_out, h_in))
+    ok_file = True
+    if rank == 0:
+        h = hashlib.sha256()
+        with open(out_path, "rb") as f:
+            while True:
+                chunk = f.read(1 << 26)
+                if not chunk:
+                    break
+                h.update(chunk)
+        ok_file = total == g["payload_bytes"] and h.hexdigest() == g["sha256"]
+    steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    t_asm = 0.0
+    for _ in range(steps):
+        n, total, ta = encode_step()
+        t_asm += ta
+    barrier()
+    t_enc = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        decode_step(n)
+    barrier()
+    t_dec = time.perf_counter() - t0
+    if state["registered"]:
+        cd.host_unregister(state["registered"][0])
+    pinned_out = bool(state["registered"])
+    del mm_arr
+    try:
+        mm.close()
+    except BufferError:
+        pass
+    os.close(fd)
+    cd.dev_free(d_pcm)
+    flags = [ok_slab, ok_table, ok_rt, ok_file]
+    if dist:
+        t = torch.tensor([t_enc, t_dec, t_asm, t_gen] + [0.0 if f else 1.0 for f in flags], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_enc, t_dec, t_asm, t_gen = (float(x) for x in t[:4])
+        flags = [float(x) == 0.0 for x in t[4:]]
+    barrier()
+    if rank == 0:
+        try:
+            os.unlink(out_path)
+        except OSError:
+            pass
+        pcm = frames_total * fb
+        res = {"workload": "BASELINE configs[3]: ONE 10 h synthetic 24-bit 48 kHz stereo file (auto LR/MS, range-addressable "
+                           f"Appendix C stream, seed 4), {nb_total} blocks sharded by contiguous block range over {world} GPU(s), "
+                           "host buffers through the C ABI; NCCL all-gather of payload byte counts -> global offsets; every "
+                           "rank writes its table slice + slab into the one .lac",
+               "pcm_bytes": pcm, "lac_bytes": g["len"], "steps": steps,
+               "encode_gbs": pcm * steps / t_enc / 1e9, "decode_gbs": pcm * steps / t_dec / 1e9,
+               "encode_decode_gbs": pcm * steps / (t_enc + t_dec) / 1e9,
+               "assemble_ms_per_step": t_asm / steps * 1e3, "output_mapping_page_locked": pinned_out, "synth_s": t_gen,
+               "slab_sha256_match_reference": flags[0], "table_sha256_match_reference": flags[1],
+               "roundtrip_exact": flags[2], "assembled_lac_sha256_match_reference": flags[3],
+               "reference_sha256": g["sha256"]}
+        assert all(flags), f"config 4 parity failed: slab/table/roundtrip/file = {flags}"
+    return res
+
+
+def kernel_src_sha() -> str:
+    """SHA-256 over the CUDA sources of the product (what a profile capture is keyed by)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "lossless-audio-codec_b200" / "csrc").glob("*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()
+
+
+def lacb_header(channels, stereo_mode, rate, depth) -> bytes:
+    """frame/frame_header.hpp:25-36 (version 3)."""
+    return bytes([0x4C, 0x41, 3, channels, stereo_mode, (rate >> 8) & 0xFF, rate & 0xFF, (rate >> 16) & 0xFF, depth, 0])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,8 +398,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=int, default=600, help="audio seconds per GPU (configs[1] = 600)")
-    ap.add_argument("--cpu-seconds", type=int, default=60, help="audio seconds of the bounded CPU sample")
+    ap.add_argument("--cpu-seconds", type=int, default=0,
+                    help="bound the CPU legs to the first N audio seconds (0 = the whole workload, the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4", choices=["auto", "on", "off"], default="auto",
+                    help="config-4 leg (the ONE 10 h file sharded over the ranks, SHA-checked against the reference): "
+                         "auto = only when --gpus > 1")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only: the line then has no e2e)")
     ap.add_argument("--e2e-contexts", type=int, default=1, help="contexts (host threads) the e2e leg splits the blocks over")
     args = ap.parse_args()
     quiet_stdout()
@@ -299,6 +507,8 @@ def main():
     h_out = cd.pinned(pcm_bytes)
     h_bb = np.zeros(nb, dtype=np.uint32)
     e2e_steps = max(1, min(args.steps, 5))
+    if args.no_e2e:
+        e2e_steps = 0
     # The block range is split over `--e2e-contexts` contexts on the same GPU, one host thread
     # each (the --threads of the GPU path): while one context's kernels run, the other's PCIe
     # copies proceed, the same overlap the reference gets from its worker pool.
@@ -334,8 +544,10 @@ def main():
                 t.join()
         return sum(sizes_out)
 
-    lac_e2e = step_host()
-    assert np.array_equal(h_out, pk), "host round trip does not restore the PCM"
+    lac_e2e = 0
+    if e2e_steps:
+        lac_e2e = step_host()
+        assert np.array_equal(h_out, pk), "host round trip does not restore the PCM"
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -348,6 +560,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall, e2e_wall = float(t[0]), float(t[1])
 
+    c4 = None
+    if args.c4 == "on" or (args.c4 == "auto" and world > 1):
+        if not dist:
+            import torch
+        c4 = run_c4(args, cd, rank, world, dist, torch)
+
     if rank == 0:
         K = args.steps
         lac = stats["lac_bytes"]
@@ -358,12 +576,13 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # DRAM bytes of one k_analyze launch from the committed `ncu --set full` capture of this same
-        # command (profiles/r1_roofline_traffic.json, written by tools/ncu_traffic.py); null without it
+        # DRAM bytes of one k_analyze launch: from the committed `ncu --set full` capture of this same command
+        # (profiles/r2_roofline_traffic.json, written by tools/ncu_traffic.py), but only while the kernel sources are
+        # the ones that capture was taken from (SHA-256 of csrc/); after any kernel change this is null until re-captured
         traffic = None
         try:
-            tj = json.loads((ROOT / "profiles" / "r1_roofline_traffic.json").read_text())
-            if tj.get("frames_per_gpu") == frames:
+            tj = json.loads((ROOT / "profiles" / "r2_roofline_traffic.json").read_text())
+            if tj.get("frames_per_gpu") == frames and tj.get("kernel_src_sha256") == kernel_src_sha():
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -389,7 +608,7 @@ def main():
             "roofline_decode": {"bound": "hbm", "kernel": "k_parse_blocks (serial bitstream parse, one warp per block)",
                                 "achieved": (pcm_bytes + lac) / parse_s / 1e9, "peak": peak, "unit": "GB/s",
                                 "frac": (pcm_bytes + lac) / parse_s / 1e9 / peak},
-            "e2e": {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,
+            "e2e": None if not e2e_steps else {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": pcm_bytes + lac_e2e, "d2h_bytes_per_step": lac_e2e + pcm_bytes,
                     "steps": e2e_steps, "contexts": nctx},
             # per step: k_deinterleave, k_plan_fixed, k_build_jobs, k_autocorr, k_levinson, k_analyze,
@@ -398,18 +617,18 @@ def main():
             "gpu_launches": K * 13,
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if c4:
+            line["c4"] = c4
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
             codec, kind = cpu_codec()
             cores = os.cpu_count() or 1
-            secs = args.cpu_seconds
-            l, r = unpack24(pk[: RATE * secs * 6])
-            te, td, _ = cpu_roundtrip(codec, l, r, cores)
-            te2, td2, _ = cpu_roundtrip(codec, l, r, cores)
+            l, r, sb, secs, what = cpu_sample(args)
+            te, td, _ = cpu_roundtrip(codec, kind, l, r, cores)
+            te2, td2, _ = cpu_roundtrip(codec, kind, l, r, cores)
             te, td = min(te, te2), min(td, td2)
-            sb = RATE * secs * 6
             line["cpu_baseline"] = {"value": sb / (te + td) / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
                                     "encode_gbs": sb / te / 1e9, "decode_gbs": sb / td / 1e9,
-                                    "sample": f"first {secs} s of the workload ({sb / 1e6:.1f} MB PCM), best of 2"}
+                                    "sample": f"{what}, best of 2, timed around LAC::Encoder::encode / LAC::Decoder::decode"}
         emit_line(line)
     cd.dev_free(d_pcm)
     cd.dev_free(d_out)

@@ -83,6 +83,11 @@ const char* lacb_last_error(const lacb_ctx* ctx);
 void lacb_free(void* p);
 int lacb_device_count(void);
 int lacb_get_timing(const lacb_ctx* ctx, lacb_timing* out);
+/* Caps the slices of whole blocks the host-buffer paths keep in flight on internal streams (the
+ * GPU path's counterpart of the reference's worker cap, LAC::Encoder::set_thread_count,
+ * src/codec/lac/encoder.cpp:385-390): 0 = automatic, 1 = one stream (copy in, kernels, copy out,
+ * nothing overlapped), n = at most n.  The bytes never depend on it. */
+int lacb_set_concurrency(lacb_ctx* ctx, uint32_t max_slices_in_flight);
 
 /* Encode `frames` frames held in HOST memory.  The block plan is the reference's:
  * fixed 16384-sample blocks, last one shorter (lac/encoder.cpp:59-69).
@@ -118,6 +123,11 @@ int lacb_dev_malloc(lacb_ctx* ctx, uint64_t bytes, void** out);
 int lacb_dev_free(lacb_ctx* ctx, void* p);
 int lacb_host_malloc(lacb_ctx* ctx, uint64_t bytes, void** out);
 int lacb_host_free(lacb_ctx* ctx, void* p);
+/* page-lock / release caller memory (e.g. a mapped output file: payload slabs and decoded PCM are then
+ * DMA-ed straight to their final place, the CLI fast path of src/main.cpp:287-311).  Registration can
+ * fail for file mappings the kernel will not pin; the pointer still works unregistered, only slower. */
+int lacb_host_register(lacb_ctx* ctx, void* p, uint64_t bytes);
+int lacb_host_unregister(lacb_ctx* ctx, void* p);
 int lacb_memcpy_h2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 int lacb_memcpy_d2h(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 int lacb_memcpy_d2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes);
@@ -136,7 +146,9 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
 /* Device-resident variant: payload and the two tables are device pointers, the planes
  * are written to d_left / d_right (device; NULL = keep them in the context workspace),
  * optional packed output to d_packed.  d_payload must be readable up to payload_bytes
- * rounded up to a multiple of 16 (the bit reader loads aligned 32-bit words). */
+ * rounded up to a multiple of 16 (the bit reader loads aligned 32-bit words).  Output contents are
+ * undefined when a decode entry point returns LACB_EDECODE (slices that finished before the failing one
+ * have been written). */
 int lacb_decode_device(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* d_payload, uint64_t payload_bytes,
                        const uint32_t* block_sizes_host, const uint32_t* block_bytes_host, uint32_t n_blocks,
                        int32_t* d_left, int32_t* d_right, uint8_t* d_packed, lacb_err* err);
@@ -147,6 +159,12 @@ int lacb_encode_block(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int zero_ru
 /* returns 1 when accepted (bits_consumed set), 0 when rejected, <0 on failure */
 int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_t block_size, int32_t* out,
                       uint64_t* bits_consumed);
+/* Same, starting `bit_offset` bits into `data` (Block::Decoder::decode_into reads from wherever the
+ * BitReader stands, src/codec/block/decoder.cpp:64); *ran_out = 1 when the rejection was "data ran out"
+ * (the reference's reader is then in its error state, bitstream/bit_reader.hpp:40-60) rather than a
+ * semantic reject. */
+int lacb_decode_block_at(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint64_t bit_offset, uint32_t block_size,
+                         int32_t* out, uint64_t* bits_consumed, int* ran_out);
 /* coeffs_out[0..order]; returns used_order (0 = unstable) or <0 */
 int lacb_lpc_analyze(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int order, int16_t* coeffs_out);
 

@@ -45,6 +45,7 @@ struct lacb_ctx {
   cudaEvent_t ev_misc = nullptr;    // hmisc has landed
   std::vector<lacb_ctx*> kids;      // slice contexts of the pipelined host paths (own stream + workspace)
   lacb_block_info last_info{};
+  uint32_t max_streams = 0;         // lacb_set_concurrency: 0 = automatic, n = at most n slices in flight
 };
 
 namespace {
@@ -274,7 +275,8 @@ bool params_ok(const lacb_enc_params* p) {
          p->stereo_mode <= 2;
 }
 
-__global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, uint32_t n, int32_t* out, u64* result) {
+__global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, u64 bit_off, uint32_t n, int32_t* out,
+                             u64* result) {
   __shared__ uint32_t ring[kDriftWin];
   __shared__ ChanHdr hdr;
   __shared__ ParseScratch sc;
@@ -282,12 +284,15 @@ __global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, uint32_t
   const uint32_t lane = threadIdx.x & 31u;
   BitRd r;
   rd_init(r, data, size, data + padded);
+  if (bit_off) rd_seek(r, r.start + bit_off);  // Block::Decoder::decode_into starts wherever the reader stands
   bool ok = parse_channel_block(r, n, out, &hdr, ring, &sc, lane);
   __syncwarp();
   if (lane != 0u) return;
+  const bool ran_out = !ok && rd_over(r);
   if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef, stage1, 1u);
   result[0] = ok ? 1ull : 0ull;
-  result[1] = ok ? rd_pos(r) - r.start : 0ull;
+  result[1] = ok ? rd_pos(r) - r.start - bit_off : 0ull;
+  result[2] = ran_out ? 1ull : 0ull;
 }
 
 }  // namespace
@@ -434,6 +439,25 @@ int lacb_host_malloc(lacb_ctx* ctx, uint64_t bytes, void** out) {
 int lacb_host_free(lacb_ctx* ctx, void* p) {
   if (!ctx) return LACB_EINVAL;
   CK(cudaFreeHost(p));
+  return 0;
+}
+// Page-locks caller memory (a mapped output file, a caller's own buffer) so that copies to / from it run at
+// full PCIe speed and asynchronously.  Fails (LACB_ECUDA) where the kernel refuses to pin the pages (writable
+// file mappings on most disk filesystems); callers then simply pass the pointer unregistered.
+int lacb_host_register(lacb_ctx* ctx, void* p, uint64_t bytes) {
+  if (!ctx || !p || !bytes) return LACB_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // not sticky: clear it
+    ctx->err = std::string("cudaHostRegister: ") + cudaGetErrorString(e);
+    return LACB_ECUDA;
+  }
+  return 0;
+}
+int lacb_host_unregister(lacb_ctx* ctx, void* p) {
+  if (!ctx || !p) return LACB_EINVAL;
+  CK(cudaHostUnregister(p));
   return 0;
 }
 int lacb_memcpy_h2d(lacb_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
@@ -665,7 +689,7 @@ static int encode_host(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, co
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
-  if (nb >= 2u * slice_blocks(ctx, prm->channels))
+  if (ctx->max_streams != 1u && nb >= 2u * slice_blocks(ctx, prm->channels))  // one stream: plain H2D, kernels, D2H
     return encode_host_sliced(ctx, prm, layout, pcm_a, pcm_b, frames, dst, dst_cap, payload_out, payload_bytes,
                               block_bytes, err);
   CKR(ensure(ctx, ctx->planeL, frames * 4));
@@ -701,11 +725,18 @@ static int encode_host(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, co
     host = (uint8_t*)malloc(total ? total : 1);
     if (!host) return LACB_ENOMEM;
   }
-  CK(cudaMemcpyAsync(host, ctx->payload.p, total, cudaMemcpyDeviceToHost, st));
-  if (block_bytes) CK(cudaMemcpyAsync(block_bytes, ctx->blk_bytes.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaEventRecord(ctx->ev[EV_D2H], st));
-  CK(cudaStreamSynchronize(st));
-  CK(cudaGetLastError());
+  const int rc_copy = [&]() -> int {
+    CK(cudaMemcpyAsync(host, ctx->payload.p, total, cudaMemcpyDeviceToHost, st));
+    if (block_bytes) CK(cudaMemcpyAsync(block_bytes, ctx->blk_bytes.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[EV_D2H], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return 0;
+  }();
+  if (rc_copy != 0) {
+    if (!dst) free(host);  // the library-owned result buffer does not outlive a failed call
+    return rc_copy;
+  }
   fill_enc_timing(ctx);
   if (payload_out) *payload_out = host;
   *payload_bytes = total;
@@ -920,6 +951,36 @@ static void fill_dec_timing(lacb_ctx* ctx) {
   t.total_ms = ev_ms(ctx, EV_START, EV_D2H);
 }
 
+// Block table checks shared by both decode entry points: sample counts in [1, 16384], at least one
+// payload byte per block (v3 tables), byte sizes that fit the payload (lac/decoder.cpp:118-137).
+static int validate_tables(lacb_ctx* ctx, const uint32_t* block_sizes, const uint32_t* block_bytes, uint32_t n_blocks,
+                           uint64_t payload_bytes, u64* frames_out, lacb_err* err) {
+  u64 frames = 0, bytes = 0;
+  for (uint32_t b = 0; b < n_blocks; ++b) {
+    if (block_sizes[b] == 0 || block_sizes[b] > kMaxBlock) {
+      ctx->err = "invalid block size";
+      set_err(err, LACB_EDECODE, b, 0, "[decode-error] invalid block size");
+      return LACB_EDECODE;
+    }
+    frames += block_sizes[b];
+    if (block_bytes) {
+      if (block_bytes[b] == 0) {
+        ctx->err = "invalid compressed block size";
+        set_err(err, LACB_EDECODE, b, 0, "[decode-error] invalid compressed block size");
+        return LACB_EDECODE;
+      }
+      bytes += block_bytes[b];
+      if (bytes > payload_bytes) {
+        ctx->err = "compressed block sizes exceed frame payload";
+        set_err(err, LACB_EDECODE, b, 0, "[decode-error] compressed block sizes exceed frame payload");
+        return LACB_EDECODE;
+      }
+    }
+  }
+  if (frames_out) *frames_out = frames;
+  return 0;
+}
+
 static bool dec_params_ok(const lacb_dec_params* p) {
   return p && (p->channels == 1 || p->channels == 2) && (p->bit_depth == 16 || p->bit_depth == 24) &&
          p->stereo_mode <= 2 && !(p->channels == 1 && p->stereo_mode != 0);
@@ -935,9 +996,9 @@ int lacb_decode_device(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t*
     return LACB_EINVAL;
   }
   CK(cudaSetDevice(ctx->device));
+  u64 frames = 0;
+  CKR(validate_tables(ctx, block_sizes_host, block_bytes_host, n_blocks, payload_bytes, &frames, err));
   if (!d_left) {  // planes are an intermediate: keep them in the context's workspace
-    u64 frames = 0;
-    for (uint32_t b = 0; b < n_blocks; ++b) frames += block_sizes_host[b];
     CKR(ensure(ctx, ctx->d_L, frames * 4));
     if (prm->channels == 2) CKR(ensure(ctx, ctx->d_R, frames * 4));
     d_left = as<int32_t>(ctx->d_L);
@@ -965,14 +1026,7 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   u64 frames = 0;
-  for (uint32_t b = 0; b < n_blocks; ++b) {
-    if (block_sizes[b] == 0 || block_sizes[b] > kMaxBlock) {
-      ctx->err = "invalid block size";
-      set_err(err, LACB_EDECODE, b, 0, "[decode-error] invalid block size");
-      return LACB_EDECODE;
-    }
-    frames += block_sizes[b];
-  }
+  CKR(validate_tables(ctx, block_sizes, block_bytes, n_blocks, payload_bytes, &frames, err));
   const uint32_t bps = prm->bit_depth / 8;
   // The parser (one warp per block) and the restore kernel (one thread per channel-block) are serial
   // chains: a launch of a few hundred blocks takes as long as one of a few thousand (measured: 2.9 ms
@@ -980,12 +1034,12 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
   // buy is the copies: with four slices in flight on four streams the host->device copy of the
   // payload and the device->host copy of the samples run under the chains of the other slices
   // (14.9 -> 12.4 ms for 600 s of 24/96 stereo; more streams than that start to share hardware queues).
-  const uint32_t nk = dec_kids();
+  const uint32_t nk = ctx->max_streams ? lacb_umin(dec_kids(), ctx->max_streams) : dec_kids();
   const uint32_t dec_sb = getenv("LACB_DEC_SLICE_BLOCKS") ? (uint32_t)atol(getenv("LACB_DEC_SLICE_BLOCKS"))
                           : getenv("LACB_SLICE_BLOCKS")   ? slice_blocks(ctx, prm->channels)
                           : n_blocks < 1024u              ? n_blocks
                                                           : lacb_umin((uint32_t)ctx->sms * 32u, (n_blocks + nk - 1u) / nk);
-  if (block_bytes && dec_sb > 0u && n_blocks > dec_sb) {
+  if (block_bytes && dec_sb > 0u && n_blocks > dec_sb && nk > 1u) {
     // pipelined: slices of whole blocks alternate between two slice contexts (see encode_host_sliced)
     CKR(ensure_kids(ctx, nk));
     const uint32_t sb = dec_sb;
@@ -1086,11 +1140,16 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
   return 0;
 }
 
-int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_t block_size, int32_t* out,
-                      uint64_t* bits_consumed) {
+int lacb_decode_block_at(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint64_t bit_offset, uint32_t block_size,
+                         int32_t* out, uint64_t* bits_consumed, int* ran_out) {
   if (!ctx || !out) return LACB_EINVAL;
   if (bits_consumed) *bits_consumed = 0;
+  if (ran_out) *ran_out = 0;
   if (block_size == 0 || block_size > kMaxBlock) return 0;
+  if (bit_offset > size * 8ull) {
+    if (ran_out) *ran_out = 1;
+    return 0;
+  }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CKR(ensure(ctx, ctx->d_payload, size + 16));
@@ -1099,16 +1158,27 @@ int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_
   if (size) CK(cudaMemcpyAsync(ctx->d_payload.p, data, size, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->d_L.p, 0, (size_t)block_size * 4, st));
   auto kd = k_decode_one;
-  LACB_LAUNCH(kd, 1, 32, 0, st, as<uint8_t>(ctx->d_payload), (u64)size, (u64)((size + 15ull) & ~15ull), block_size,
-              as<int32_t>(ctx->d_L),
-              as<u64>(ctx->misc));
-  u64 res[2] = {0, 0};
-  CK(cudaMemcpyAsync(res, ctx->misc.p, 16, cudaMemcpyDeviceToHost, st));
+  LACB_LAUNCH(kd, 1, 32, 0, st, as<uint8_t>(ctx->d_payload), (u64)size, (u64)((size + 15ull) & ~15ull), (u64)bit_offset,
+              block_size, as<int32_t>(ctx->d_L), as<u64>(ctx->misc));
+  u64 res[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(res, ctx->misc.p, 24, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(out, ctx->d_L.p, (size_t)block_size * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   CK(cudaGetLastError());
   if (bits_consumed) *bits_consumed = res[1];
+  if (ran_out) *ran_out = res[2] ? 1 : 0;
   return res[0] ? 1 : 0;
+}
+
+int lacb_decode_block(lacb_ctx* ctx, const uint8_t* data, uint64_t size, uint32_t block_size, int32_t* out,
+                      uint64_t* bits_consumed) {
+  return lacb_decode_block_at(ctx, data, size, 0, block_size, out, bits_consumed, nullptr);
+}
+
+int lacb_set_concurrency(lacb_ctx* ctx, uint32_t max_slices_in_flight) {
+  if (!ctx) return LACB_EINVAL;
+  ctx->max_streams = max_slices_in_flight;
+  return 0;
 }
 
 }  // extern "C"

@@ -26,7 +26,7 @@ void usage() {
   std::cerr << "Usage:\n"
             << "  lac_cli encode input.wav output.lac [--stereo-mode=lr|ms] [--threads=N] [--devices=N] "
                "[--debug-threads] [--no-partitioning] [--allow-large]\n"
-            << "  lac_cli decode input.lac output.wav [--threads=N] [--debug-threads]\n"
+            << "  lac_cli decode input.lac output.wav [--threads=N] [--devices=N] [--debug-threads] [--allow-large]\n"
             << "  lac_cli selftest\n"
             << "  lac_cli batch list.txt        (one encode/decode command per line, one process)\n";
 }
@@ -39,21 +39,6 @@ size_t parse_count_flag(const std::string& arg, const char* name) {
   const unsigned long long n = std::stoull(v);
   if (n == 0) throw std::invalid_argument(std::string(name) + " requires a positive integer");
   return (size_t)n;
-}
-
-bool load_file(const std::string& path, std::vector<uint8_t>& out, uint64_t cap) {
-  FILE* f = std::fopen(path.c_str(), "rb");
-  if (!f) return false;
-  std::fseek(f, 0, SEEK_END);
-  const long long n = std::ftell(f);
-  std::rewind(f);
-  bool ok = n >= 0 && (uint64_t)n <= cap;
-  if (ok) {
-    out.resize((size_t)n);
-    ok = n == 0 || std::fread(out.data(), 1, (size_t)n, f) == (size_t)n;
-  }
-  std::fclose(f);
-  return ok;
 }
 
 // Output is written inside a private (0700) temporary directory next to the destination and
@@ -94,13 +79,6 @@ bool same_file(const std::string& a, const std::string& b) {
   std::error_code ec;
   if (!std::filesystem::exists(b, ec)) return false;
   return std::filesystem::equivalent(a, b, ec) && !ec;
-}
-
-bool save_file(const std::string& path, const std::vector<uint8_t>& bytes) {
-  FILE* f = std::fopen(path.c_str(), "wb");
-  if (!f) return false;
-  const bool ok = bytes.empty() || std::fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
-  return (std::fclose(f) == 0) && ok;
 }
 
 void print_threads(const char* label, const LAC::ThreadCollector& tc) {
@@ -239,57 +217,79 @@ static int run_command(int argc, char** argv) {
     if (threads == 0) threads = LAC::parse_thread_limit(std::getenv("LAC_THREADS"));
 
     if (cmd == "encode") {
+      // the input WAV is mapped, not read: the device de-interleaves the data chunk where it lies
+      MappedFile in;
       WavInfo info;
-      std::vector<uint8_t> pcm;
-      if (!read_wav_packed(in_path, info, pcm, allow_large)) {
+      uint64_t data_off = 0, data_bytes = 0;
+      if (!in.open_read(in_path) || !locate_wav_data(in.data, in.size, info, data_off, data_bytes, allow_large)) {
         std::cerr << "Failed to read WAV: " << in_path << "\n";
         return 1;
       }
-      milestone("wav read");
+      milestone("wav mapped");
       LAC::ThreadCollector tc;
       LAC::Encoder enc(12, stereo_mode, info.sample_rate, info.bit_depth);
       enc.set_partitioning_enabled(partitioning);
       enc.set_thread_count(threads);
       enc.set_device_count(devices);
-      const std::vector<uint8_t> bitstream = enc.encode_packed(pcm.data(), info.frames, (uint8_t)info.channels, &tc);
-      milestone("encoded");
       Staged st(out_path);
-      if (!st.ok || !save_file(st.tmp_path.string(), bitstream) || !st.publish()) {
+      if (!st.ok) {
+        std::cerr << "Failed to write LAC file: " << out_path << "\n";
+        return 1;
+      }
+      uint64_t lac_bytes = 0;
+      try {
+        lac_bytes = enc.encode_packed_to_file(in.data + data_off, info.frames, (uint8_t)info.channels,
+                                              st.tmp_path.string(), &tc);
+      } catch (const std::runtime_error& e) {
+        if (std::string(e.what()).rfind("failed to", 0) == 0) {
+          std::cerr << "Failed to write LAC file: " << out_path << "\n";
+          return 1;
+        }
+        throw;
+      }
+      milestone("encoded");
+      if (!st.publish()) {
         std::cerr << "Failed to write LAC file: " << out_path << "\n";
         return 1;
       }
       milestone("lac written");
-      std::cout << "Encoded " << in_path << " -> " << out_path << " (" << bitstream.size() << " bytes)\n";
+      std::cout << "Encoded " << in_path << " -> " << out_path << " (" << lac_bytes << " bytes)\n";
       if (debug_threads) print_threads("Thread usage", tc);
       return 0;
     }
 
-    std::vector<uint8_t> lac;
-    if (!load_file(in_path, lac, 1ull << 30)) {
+    // decode: the .lac is mapped, the WAV is created at its final size, mapped, and filled by the device
+    // (the reference's mmap fast path, src/main.cpp:184-430)
+    MappedFile lac;
+    if (!lac.open_read(in_path) || (!allow_large && lac.size > (1ull << 30))) {  // MAX_LAC_INPUT_BYTES, main.cpp:40
       std::cerr << "Failed to read LAC file: " << in_path << "\n";
       return 1;
     }
-    milestone("lac read");
+    milestone("lac mapped");
     LAC::ThreadCollector tc;
     LAC::Decoder dec(&tc);
     dec.set_thread_count(threads);
-    std::vector<uint8_t> pcm;
+    dec.set_device_count(devices);
+    dec.set_allow_large(allow_large);
     FrameHeader hdr;
     uint64_t frames = 0;
+    Staged st(out_path);
+    if (!st.ok) {
+      std::cerr << "Failed to write WAV: " << out_path << "\n";
+      return 1;
+    }
     try {
-      dec.decode_packed(lac.data(), lac.size(), pcm, hdr, frames);
+      dec.decode_packed_to_file(lac.data, lac.size, st.tmp_path.string(), hdr, frames);
     } catch (const std::runtime_error& e) {
+      if (std::string(e.what()).rfind("failed to", 0) == 0) {
+        std::cerr << "Failed to write WAV: " << out_path << "\n";
+        return 1;
+      }
       std::cerr << "Decode failed: " << e.what() << "\n";
       return 1;
     }
     milestone("decoded");
-    WavInfo info;
-    info.channels = hdr.channels;
-    info.sample_rate = hdr.sample_rate;
-    info.bit_depth = hdr.bit_depth;
-    info.frames = frames;
-    Staged st(out_path);
-    if (!st.ok || !write_wav_packed(st.tmp_path.string(), info, pcm.data(), pcm.size()) || !st.publish()) {
+    if (!st.publish()) {
       std::cerr << "Failed to write WAV: " << out_path << "\n";
       return 1;
     }

@@ -128,13 +128,20 @@ class Encoder {
   std::vector<uint8_t> encode_packed(const uint8_t* pcm, uint64_t frames, uint8_t channels,
                                      ThreadCollector* collector = nullptr);
 
+  // GPU-path extension, the CLI's encode path: the .lac is written through a mapping of `path` (payload bytes go
+  // device -> file, no intermediate vector).  Returns the .lac size.
+  uint64_t encode_packed_to_file(const uint8_t* pcm, uint64_t frames, uint8_t channels, const std::string& path,
+                                 ThreadCollector* collector = nullptr);
+
   void set_zero_run_enabled(bool enabled) { zero_run_enabled_ = enabled; }
   void set_partitioning_enabled(bool enabled) { partitioning_enabled_ = enabled; }
   void set_debug_partitions(bool enabled) { debug_partitions_ = enabled; }
+  // worker cap of the reference (0 = automatic): bounds the devices used and the slices in flight per device
   void set_thread_count(size_t max_threads) { thread_count_ = max_threads; }
   void set_device_count(size_t devices) { device_count_ = devices; }  // 0 = LAC_DEVICES or 1
 
  private:
+  void check_config() const;
   std::vector<uint8_t> run(int layout, const void* a, const void* b, uint64_t frames, uint8_t channels,
                            ThreadCollector* collector);
   uint8_t order_;  // accepted and ignored, exactly like the reference
@@ -157,11 +164,21 @@ class Decoder {
   // src/main.cpp:184-430); `out` must hold frames * channels * bit_depth/8 bytes.
   void decode_packed(const uint8_t* data, size_t size, std::vector<uint8_t>& out, FrameHeader& hdr,
                      uint64_t& frames);
+  // GPU-path extension, the CLI fast path with a mapped output (src/main.cpp:287-311,386-393): the WAV (RF64 when
+  // large files are allowed and RIFF cannot hold it) is created at `path` and the device packs the samples
+  // straight into the mapping.
+  void decode_packed_to_file(const uint8_t* data, size_t size, const std::string& path, FrameHeader& hdr,
+                             uint64_t& frames);
   void set_thread_count(size_t max_threads) { thread_count_ = max_threads; }
+  void set_device_count(size_t devices) { device_count_ = devices; }  // 0 = LAC_DEVICES or 1
+  // lifts the reference's 1 GiB decoded-PCM cap and the RIFF size cap; off by default
+  void set_allow_large(bool allow) { allow_large_ = allow; }
 
  private:
   ThreadCollector* collector_;
   size_t thread_count_ = 0;
+  size_t device_count_ = 0;
+  bool allow_large_ = false;
 };
 
 }  // namespace LAC
@@ -199,7 +216,7 @@ class Decoder {
  public:
   Decoder() = default;
   bool decode(BitReader& br, uint32_t block_size, std::vector<int32_t>& out);
-  // The reader must be byte aligned (every call site in the reference is).
+  // Decodes from wherever the reader stands (any bit position).
   bool decode_into(BitReader& br, uint32_t block_size, int32_t* out);
 };
 

@@ -1,5 +1,10 @@
 #include "wav_io.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstring>
 
@@ -15,38 +20,87 @@ struct File {
   explicit File(const char* path, const char* mode) : f(std::fopen(path, mode)) {}
   ~File() { if (f) std::fclose(f); }
 };
+
+uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+void put64(uint8_t* p, uint64_t v) { put32(p, (uint32_t)v); put32(p + 4, (uint32_t)(v >> 32)); }
 }  // namespace
 
-bool read_wav_packed(const std::string& path, WavInfo& info, std::vector<uint8_t>& pcm, bool allow_large) {
-  info = WavInfo{};
-  pcm.clear();
-  File file(path.c_str(), "rb");
-  if (!file.f) return false;
-  if (std::fseek(file.f, 0, SEEK_END) != 0) return false;
-  const long long end = std::ftell(file.f);
-  if (end < 12) return false;
-  const uint64_t file_size = (uint64_t)end;
-  std::rewind(file.f);
-  uint8_t hdr[12];
-  if (std::fread(hdr, 1, 12, file.f) != 12) return false;
-  if (std::memcmp(hdr, "RIFF", 4) != 0 || std::memcmp(hdr + 8, "WAVE", 4) != 0) return false;
-  if ((uint64_t)le32(hdr + 4) + 8u != file_size) return false;
+bool MappedFile::open_read(const std::string& path) {
+  close();
+  fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) return false;
+  struct stat st;
+  if (::fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) { close(); return false; }
+  size = (uint64_t)st.st_size;
+  if (size == 0) return true;  // empty file: valid handle, nothing mapped
+  void* p = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+  if (p == MAP_FAILED) { close(); return false; }
+  data = static_cast<uint8_t*>(p);
+  return true;
+}
+bool MappedFile::create(const std::string& path, uint64_t bytes) {
+  close();
+  fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
+  if (fd < 0) return false;
+  if (::ftruncate(fd, (off_t)bytes) != 0) { close(); return false; }
+  size = bytes;
+  writable = true;
+  if (bytes == 0) return true;
+  void* p = ::mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (p == MAP_FAILED) { close(); return false; }
+  data = static_cast<uint8_t*>(p);
+  return true;
+}
+bool MappedFile::resize(uint64_t bytes) {
+  if (fd < 0 || !writable) return false;
+  if (data) ::munmap(data, size);
+  data = nullptr;
+  size = 0;
+  return ::ftruncate(fd, (off_t)bytes) == 0;
+}
+void MappedFile::close() {
+  if (data) ::munmap(data, size);
+  if (fd >= 0) ::close(fd);
+  data = nullptr;
+  size = 0;
+  fd = -1;
+  writable = false;
+}
 
+bool locate_wav_data(const uint8_t* file, uint64_t file_size, WavInfo& info, uint64_t& data_offset,
+                     uint64_t& data_bytes, bool allow_large) {
+  info = WavInfo{};
+  data_offset = data_bytes = 0;
+  if (!file || file_size < 12) return false;
+  const bool rf64 = std::memcmp(file, "RF64", 4) == 0;
+  if ((!rf64 && std::memcmp(file, "RIFF", 4) != 0) || std::memcmp(file + 8, "WAVE", 4) != 0) return false;
+  if (rf64 && !allow_large) return false;  // the reference knows classic RIFF only (src/io/wav_io.cpp:190-200)
+  uint64_t riff_size = le32(file + 4), ds64_data = 0;
+  bool got_ds64 = false;
   bool got_fmt = false, got_data = false;
   uint16_t block_align = 0;
-  uint64_t remaining = file_size - 12u;
-  while (remaining > 0) {
-    if (remaining < 8u) return false;
-    uint8_t ch[8];
-    if (std::fread(ch, 1, 8, file.f) != 8) return false;
-    remaining -= 8u;
-    const uint32_t size = le32(ch + 4);
-    const uint64_t padded = (uint64_t)size + (size & 1u);
-    if (padded > remaining) return false;
+  uint64_t pos = 12;
+  if (rf64) {  // 'ds64' must be the first chunk: riffSize, dataSize, sampleCount (u64 each), tableLength (u32)
+    if (file_size < pos + 8 + 28 || std::memcmp(file + pos, "ds64", 4) != 0) return false;
+    const uint32_t sz = le32(file + pos + 4);
+    if (sz < 28 || (uint64_t)sz + (sz & 1u) > file_size - pos - 8) return false;
+    riff_size = le64(file + pos + 8);
+    ds64_data = le64(file + pos + 16);
+    got_ds64 = true;
+    pos += 8 + (uint64_t)sz + (sz & 1u);
+  }
+  if (riff_size + 8u != file_size) return false;
+  while (pos < file_size) {
+    if (file_size - pos < 8u) return false;
+    const uint8_t* ch = file + pos;
+    pos += 8u;
+    uint64_t size = le32(ch + 4);
+    if (got_ds64 && std::memcmp(ch, "data", 4) == 0 && size == 0xFFFFFFFFull) size = ds64_data;
+    const uint64_t padded = size + (size & 1u);
+    if (padded > file_size - pos) return false;
     if (std::memcmp(ch, "fmt ", 4) == 0) {
       if (got_fmt || got_data || size != 16u) return false;
-      uint8_t f[16];
-      if (std::fread(f, 1, 16, file.f) != 16) return false;
+      const uint8_t* f = file + pos;
       const uint16_t format = le16(f), channels = le16(f + 2), align = le16(f + 12), bits = le16(f + 14);
       const uint32_t rate = le32(f + 4), byte_rate = le32(f + 8);
       if (format != 1 || (bits != 16 && bits != 24) || !rate_ok(rate) || (channels != 1 && channels != 2)) return false;
@@ -61,21 +115,60 @@ bool read_wav_packed(const std::string& path, WavInfo& info, std::vector<uint8_t
       if (!got_fmt || got_data || size == 0u || size % block_align != 0) return false;
       const uint64_t frames = size / block_align;
       if (!allow_large && frames * info.channels * 4ull > kMaxDecodedPcmBytes) return false;
-      pcm.resize(size);
-      if (std::fread(pcm.data(), 1, size, file.f) != size) return false;
       info.frames = frames;
+      data_offset = pos;
+      data_bytes = size;
       got_data = true;
-    } else {
-      if (std::fseek(file.f, (long)size, SEEK_CUR) != 0) return false;
     }
-    if ((size & 1u) && std::fseek(file.f, 1, SEEK_CUR) != 0) return false;
-    remaining -= padded;
+    pos += padded;
   }
-  if (!got_fmt || !got_data) {
-    pcm.clear();
-    return false;
-  }
+  return got_fmt && got_data;
+}
+
+bool read_wav_packed(const std::string& path, WavInfo& info, std::vector<uint8_t>& pcm, bool allow_large) {
+  info = WavInfo{};
+  pcm.clear();
+  MappedFile mf;
+  if (!mf.open_read(path) || mf.size < 12) return false;
+  uint64_t off = 0, bytes = 0;
+  if (!locate_wav_data(mf.data, mf.size, info, off, bytes, allow_large)) return false;
+  pcm.assign(mf.data + off, mf.data + off + bytes);
   return true;
+}
+
+std::vector<uint8_t> wav_header(const WavInfo& info, uint64_t pcm_bytes, bool* rf64_out) {
+  const uint64_t pad = pcm_bytes & 1u;
+  const bool rf64 = 36u + pcm_bytes + pad > 0xFFFFFFFFull;
+  if (rf64_out) *rf64_out = rf64;
+  const uint16_t align = (uint16_t)(info.channels * (info.bit_depth / 8));
+  std::vector<uint8_t> h(rf64 ? 80 : 44, 0);
+  uint8_t* p = h.data();
+  if (rf64) {
+    std::memcpy(p, "RF64", 4);
+    put32(p + 4, 0xFFFFFFFFu);
+    std::memcpy(p + 8, "WAVEds64", 8);
+    put32(p + 16, 28);
+    put64(p + 20, 72u + pcm_bytes + pad);  // riff size: everything after the first 8 bytes
+    put64(p + 28, pcm_bytes);
+    put64(p + 36, pcm_bytes / align);      // sample (frame) count
+    put32(p + 44, 0);                      // no chunk-size table
+    p += 36;                               // "fmt " starts at byte 48
+  } else {
+    std::memcpy(p, "RIFF", 4);
+    put32(p + 4, (uint32_t)(36u + pcm_bytes + pad));
+    std::memcpy(p + 8, "WAVE", 4);
+  }
+  std::memcpy(p + 12, "fmt ", 4);
+  put32(p + 16, 16);
+  put16(p + 20, 1);
+  put16(p + 22, info.channels);
+  put32(p + 24, info.sample_rate);
+  put32(p + 28, info.sample_rate * align);
+  put16(p + 32, align);
+  put16(p + 34, info.bit_depth);
+  std::memcpy(p + 36, "data", 4);
+  put32(p + 40, rf64 ? 0xFFFFFFFFu : (uint32_t)pcm_bytes);
+  return h;
 }
 
 bool write_wav_packed(const std::string& path, const WavInfo& info, const uint8_t* pcm, uint64_t pcm_bytes) {
@@ -84,23 +177,10 @@ bool write_wav_packed(const std::string& path, const WavInfo& info, const uint8_
     return false;
   const uint64_t pad = pcm_bytes & 1u;
   if (36u + pcm_bytes + pad > 0xFFFFFFFFull) return false;  // classic RIFF limit (src/io/wav_io.cpp:309)
-  uint8_t h[44];
-  std::memcpy(h, "RIFF", 4);
-  put32(h + 4, (uint32_t)(36u + pcm_bytes + pad));
-  std::memcpy(h + 8, "WAVEfmt ", 8);
-  put32(h + 16, 16);
-  put16(h + 20, 1);
-  put16(h + 22, info.channels);
-  put32(h + 24, info.sample_rate);
-  const uint16_t align = (uint16_t)(info.channels * (info.bit_depth / 8));
-  put32(h + 28, info.sample_rate * align);
-  put16(h + 32, align);
-  put16(h + 34, info.bit_depth);
-  std::memcpy(h + 36, "data", 4);
-  put32(h + 40, (uint32_t)pcm_bytes);
+  const std::vector<uint8_t> h = wav_header(info, pcm_bytes);
   File file(path.c_str(), "wb");
   if (!file.f) return false;
-  if (std::fwrite(h, 1, 44, file.f) != 44) return false;
+  if (std::fwrite(h.data(), 1, h.size(), file.f) != h.size()) return false;
   if (pcm_bytes && std::fwrite(pcm, 1, pcm_bytes, file.f) != pcm_bytes) return false;
   const uint8_t zero = 0;
   if (pad && std::fwrite(&zero, 1, 1, file.f) != 1) return false;

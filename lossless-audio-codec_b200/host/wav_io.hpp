@@ -24,6 +24,31 @@ constexpr uint64_t kMaxDecodedPcmBytes = 1ull << 30;  // src/io/wav_io.cpp:13 (i
 // 1 GiB decoded-PCM cap (needed for BASELINE configs 3 and 4).
 bool read_wav_packed(const std::string& path, WavInfo& info, std::vector<uint8_t>& pcm, bool allow_large = false);
 bool write_wav_packed(const std::string& path, const WavInfo& info, const uint8_t* pcm, uint64_t pcm_bytes);
+// --- mapped-file forms (CLI fast paths) --------------------------------------
+// A read-only mapping of a whole file, or a writable MAP_SHARED mapping of a file created at a given size.
+struct MappedFile {
+  uint8_t* data = nullptr;
+  uint64_t size = 0;
+  int fd = -1;
+  bool writable = false;
+  MappedFile() = default;
+  MappedFile(const MappedFile&) = delete;
+  MappedFile& operator=(const MappedFile&) = delete;
+  ~MappedFile() { close(); }
+  bool open_read(const std::string& path);
+  bool create(const std::string& path, uint64_t bytes);
+  bool resize(uint64_t bytes);  // shrinks / grows the file; the mapping is dropped (call before close)
+  void close();
+};
+// Parses the RIFF / RF64 structure of a WAV held in memory (same accept / reject rules as read_wav_packed) and
+// returns where the sample bytes are: nothing is copied.  RF64 (EBU Tech 3306: 'RF64' + 'ds64' chunk carrying the
+// 64-bit riff / data sizes) is accepted only with allow_large, like every size above the reference's 1 GiB cap.
+bool locate_wav_data(const uint8_t* file, uint64_t file_size, WavInfo& info, uint64_t& data_offset,
+                     uint64_t& data_bytes, bool allow_large);
+// Header of a WAV with pcm_bytes of samples: 44 bytes of classic RIFF, or 80 bytes of RF64 when the RIFF size
+// field cannot hold it (only produced when the caller opted in to large files).
+std::vector<uint8_t> wav_header(const WavInfo& info, uint64_t pcm_bytes, bool* rf64 = nullptr);
+
 // int32 plane variants for callers that hold planes (LAC::Decoder::decode output)
 bool write_wav_planes(const std::string& path, const WavInfo& info, const std::vector<int32_t>& left,
                       const std::vector<int32_t>& right);

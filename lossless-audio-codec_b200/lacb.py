@@ -57,7 +57,8 @@ class BlockInfo(C.Structure):
 EXPORTS = ("lacb_create", "lacb_destroy", "lacb_last_error", "lacb_free", "lacb_device_count", "lacb_get_timing",
            "lacb_encode", "lacb_encode_to", "lacb_encode_device", "lacb_decode", "lacb_decode_device", "lacb_encode_block",
            "lacb_decode_block", "lacb_lpc_analyze", "lacb_last_block_info", "lacb_dev_malloc", "lacb_dev_free",
-           "lacb_host_malloc", "lacb_host_free", "lacb_memcpy_h2d", "lacb_memcpy_d2h", "lacb_memcpy_d2d")
+           "lacb_host_malloc", "lacb_host_free", "lacb_memcpy_h2d", "lacb_memcpy_d2h", "lacb_memcpy_d2d",
+           "lacb_decode_block_at", "lacb_set_concurrency", "lacb_host_register", "lacb_host_unregister")
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -93,12 +94,17 @@ def load_library(path=None) -> C.CDLL:
     lib.lacb_encode_block.argtypes = [C.c_void_p, i32p, C.c_uint32, C.c_int, C.c_int, C.POINTER(u8p),
                                       C.POINTER(C.c_uint64)]
     lib.lacb_decode_block.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, i32p, C.POINTER(C.c_uint64)]
+    lib.lacb_decode_block_at.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, i32p,
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+    lib.lacb_set_concurrency.argtypes = [C.c_void_p, C.c_uint32]
     lib.lacb_lpc_analyze.argtypes = [C.c_void_p, i32p, C.c_uint32, C.c_int, C.POINTER(C.c_int16)]
     lib.lacb_last_block_info.argtypes = [C.c_void_p, C.POINTER(BlockInfo)]
     lib.lacb_dev_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lacb_dev_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.lacb_host_malloc.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
     lib.lacb_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lacb_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.lacb_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
     for fn in (lib.lacb_memcpy_h2d, lib.lacb_memcpy_d2h, lib.lacb_memcpy_d2d):
         fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     return lib
@@ -185,6 +191,17 @@ class Codec:
         if self.lib.lacb_memcpy_d2h(self.h, out.ctypes.data, C.c_void_p(dptr), nbytes) != 0:
             raise RuntimeError("lacb_memcpy_d2h: " + self.last_error())
         return out
+
+    def d2h_to(self, host_ptr: int, dptr: int, nbytes: int):
+        """device -> host copy to a raw host address (e.g. inside a mapped, registered output file)"""
+        if self.lib.lacb_memcpy_d2h(self.h, C.c_void_p(host_ptr), C.c_void_p(dptr), nbytes) != 0:
+            raise RuntimeError("lacb_memcpy_d2h: " + self.last_error())
+
+    def host_register(self, host_ptr: int, nbytes: int) -> bool:
+        return self.lib.lacb_host_register(self.h, C.c_void_p(host_ptr), nbytes) == 0
+
+    def host_unregister(self, host_ptr: int):
+        self.lib.lacb_host_unregister(self.h, C.c_void_p(host_ptr))
 
     def d2d(self, dst: int, src: int, nbytes: int):
         if self.lib.lacb_memcpy_d2d(self.h, C.c_void_p(dst), C.c_void_p(src), nbytes) != 0:
@@ -418,6 +435,20 @@ class Codec:
         if rc < 0:
             raise RuntimeError(f"lacb_decode_block rc={rc}: {self.last_error()}")
         return bool(rc), out[:block_size], bits.value
+
+    def block_decode_at(self, data: bytes, bit_offset: int, block_size: int):
+        """Block::Decoder::decode_into from an arbitrary bit position -> (ok, pcm, bits consumed, ran_out)."""
+        buf = np.frombuffer(data if data else b"\0", dtype=np.uint8)
+        out = np.zeros(max(1, block_size), dtype=np.int32)
+        bits, ran = C.c_uint64(), C.c_int()
+        rc = self.lib.lacb_decode_block_at(self.h, buf.ctypes.data, len(data), bit_offset, block_size,
+                                           out.ctypes.data_as(i32p), C.byref(bits), C.byref(ran))
+        if rc < 0:
+            raise RuntimeError(f"lacb_decode_block_at rc={rc}: {self.last_error()}")
+        return bool(rc), out[:block_size], bits.value, bool(ran.value)
+
+    def set_concurrency(self, n: int):
+        self.lib.lacb_set_concurrency(self.h, n)
 
     def lpc_analyze(self, pcm, order: int):
         a = np.ascontiguousarray(pcm, dtype=np.int32)

@@ -11,6 +11,7 @@
 //   Block::Encoder::encode          src/codec/block/encoder.cpp:313
 //   Block::Decoder::decode_into     src/codec/block/decoder.cpp:64
 //   LPC::analyze_block_q15          src/codec/lpc/lpc.cpp:156
+#include <chrono>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +59,53 @@ int ref_encode(const int32_t* left, const int32_t* right, uint64_t frames,
     *out = dup_bytes(bytes);
     *out_size = bytes.size();
     return *out ? 0 : -2;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return -1;
+  }
+}
+
+// Timed variants for bench.py's reference arm / cpu_baseline leg: the std::vector copies of the
+// caller's planes (an artefact of calling the C++ interface through C) are made BEFORE the clock
+// starts, so *seconds covers LAC::Encoder::encode / LAC::Decoder::decode and nothing else.
+int ref_encode_timed(const int32_t* left, const int32_t* right, uint64_t frames,
+                     uint32_t sample_rate, uint32_t bit_depth, uint32_t stereo_mode,
+                     uint32_t threads, uint8_t** out, uint64_t* out_size, double* seconds) {
+  try {
+    std::vector<int32_t> l(left, left + frames);
+    std::vector<int32_t> r;
+    if (right) r.assign(right, right + frames);
+    LAC::Encoder enc(12, static_cast<uint8_t>(stereo_mode), sample_rate,
+                     static_cast<uint8_t>(bit_depth));
+    enc.set_thread_count(threads);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint8_t> bytes = enc.encode(l, r);
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    *out = dup_bytes(bytes);
+    *out_size = bytes.size();
+    return *out ? 0 : -2;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return -1;
+  }
+}
+
+// Decodes `data`, timing LAC::Decoder::decode only, and compares the result with the expected
+// planes (*match = 1 when identical; expect_r NULL for mono).
+int ref_decode_timed(const uint8_t* data, uint64_t size, uint32_t threads, const int32_t* expect_l,
+                     const int32_t* expect_r, uint64_t frames, double* seconds, int* match) {
+  try {
+    LAC::Decoder dec;
+    dec.set_thread_count(threads);
+    std::vector<int32_t> l, r;
+    const auto t0 = std::chrono::steady_clock::now();
+    dec.decode(data, size, l, r, nullptr);
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    bool ok = l.size() == frames && std::memcmp(l.data(), expect_l, sizeof(int32_t) * frames) == 0;
+    if (expect_r) ok = ok && r.size() == frames && std::memcmp(r.data(), expect_r, sizeof(int32_t) * frames) == 0;
+    else ok = ok && r.empty();
+    *match = ok ? 1 : 0;
+    return 0;
   } catch (const std::exception& e) {
     g_last_error = e.what();
     return -1;

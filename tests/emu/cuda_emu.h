@@ -341,6 +341,9 @@ static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 2; }
 template <typename T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMallocHost(p, n); }
+enum { cudaHostRegisterPortable = 1 };
+static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return 0; }
+static inline cudaError_t cudaHostUnregister(void*) { return 0; }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { if (n) memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) memcpy(d, s, n); return 0; }

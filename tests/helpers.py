@@ -197,6 +197,41 @@ def synth(seed: int, frames: int, depth: int, channels: int = 2, want_packed=Fal
     return (left, right, packed) if want_packed else (left, right)
 
 
+C4_RESET_LOG2 = 19  # config 4's range-addressable stream: filter state reset every 2^19 frames (tools/lac_synth.c)
+
+
+def synth_lib():
+    global _synth
+    if _synth is None:
+        _build_if_missing()
+        _synth = C.CDLL(str(SYNTH_SO))
+        _synth.lac_synth.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.c_int, i32p, i32p, u8p]
+        _synth.lac_synth.restype = None
+    if not hasattr(_synth, "_range_ready"):
+        _synth.lac_synth_range.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                           i32p, i32p, u8p]
+        _synth.lac_synth_range.restype = None
+        _synth._range_ready = True
+    return _synth
+
+
+def synth_range(seed: int, f0: int, frames: int, depth: int, channels: int = 2, reset_log2: int = C4_RESET_LOG2,
+                planes=True, want_packed=False):
+    """Frames [f0, f0+frames) of the range-addressable stream (config 4).  Returns (left, right[, packed]);
+    planes=False skips the int32 planes (returns (None, None, packed))."""
+    lib = synth_lib()
+    left = np.zeros(frames, dtype=np.int32) if planes else None
+    right = np.zeros(frames, dtype=np.int32) if planes else None
+    packed = np.zeros(frames * channels * (depth // 8), dtype=np.uint8) if want_packed else None
+    lib.lac_synth_range(seed, f0, frames, depth, channels, reset_log2,
+                        left.ctypes.data_as(i32p) if planes else None,
+                        right.ctypes.data_as(i32p) if planes else None,
+                        packed.ctypes.data_as(u8p) if want_packed else None)
+    if channels == 1 and planes:
+        right = np.zeros(0, dtype=np.int32)
+    return (left, right, packed) if want_packed else (left, right)
+
+
 # ---------------------------------------------------------------------------
 # deterministic parity corpus (shapes follow the reference's own test inputs;
 # see SURVEY.md section 8(c) for the file:line of each family)

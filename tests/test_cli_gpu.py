@@ -106,3 +106,57 @@ def test_batch_mode(cli, tmp_path):
     (tmp_path / "o0.lac").unlink()
     res = _run(cli, "batch", str(lst))
     assert res.returncode == 1 and (tmp_path / "o0.lac").exists()
+
+
+def test_threads_flag_is_honoured(cli, tmp_path):
+    """--threads caps the workers (src/main.cpp:560-591): 1 = one device, one stream; the bytes do not depend on it."""
+    l, r, pk = H.synth(3, 6 * 16384 + 5, 24, want_packed=True)
+    wav = tmp_path / "in.wav"
+    _write_wav(wav, pk, 2, 96000, 24)
+    outs = []
+    for t in ("--threads=1", "--threads=7"):
+        lac = tmp_path / f"o{t[-1]}.lac"
+        res = _run(cli, "encode", str(wav), str(lac), t, "--debug-threads")
+        assert res.returncode == 0, res.stderr
+        assert "Thread usage: 1 threads" in res.stdout  # one device => one worker, whatever the cap
+        outs.append(lac.read_bytes())
+        res = _run(cli, "decode", str(lac), str(tmp_path / "b.wav"), t, "--debug-threads")
+        assert res.returncode == 0 and "Decoder thread usage: 1 threads" in res.stdout
+        assert (tmp_path / "b.wav").read_bytes() == wav.read_bytes()
+    assert outs[0] == outs[1] == H.oracle().encode(l, r, 96000, 24, 2)
+
+
+def _rf64(packed: np.ndarray, channels, rate, depth) -> bytes:
+    """EBU Tech 3306 RF64 form of a (small) WAV: ds64 chunk with the 64-bit sizes, 0xFFFFFFFF in the 32-bit fields"""
+    align = channels * depth // 8
+    n = packed.size
+    ds64 = struct.pack("<QQQI", 72 + n + (n & 1), n, n // align, 0)
+    return (b"RF64" + struct.pack("<I", 0xFFFFFFFF) + b"WAVEds64" + struct.pack("<I", 28) + ds64 + b"fmt " +
+            struct.pack("<IHHIIHH", 16, 1, channels, rate, rate * align, align, depth) + b"data" +
+            struct.pack("<I", 0xFFFFFFFF) + packed.tobytes() + (b"\0" if n & 1 else b""))
+
+
+def test_rf64_input_needs_allow_large(cli, tmp_path):
+    l, r, pk = H.synth(5, 3 * 16384 + 1, 24, want_packed=True)
+    wav, lac = tmp_path / "in.rf64.wav", tmp_path / "o.lac"
+    wav.write_bytes(_rf64(pk, 2, 48000, 24))
+    assert _run(cli, "encode", str(wav), str(lac)).returncode == 1 and not lac.exists()
+    res = _run(cli, "encode", str(wav), str(lac), "--allow-large")
+    assert res.returncode == 0, res.stderr
+    assert lac.read_bytes() == H.oracle().encode(l, r, 48000, 24, 2)
+
+
+def test_decode_size_cap_and_opt_in(cli, tmp_path):
+    """A table that declares more than 1 GiB of int32 PCM is rejected before anything is allocated, exactly like the
+    reference CLI (src/main.cpp:247-251); --allow-large is the explicit opt-in."""
+    nb = 65536 + 512  # x 16384 samples x 4 bytes > 1 GiB, mono
+    table = np.empty((nb, 2), dtype=">u4")
+    table[:, 0], table[:, 1] = 16384, 1
+    crafted = H.lacb_module().FrameHeader(1, 0, 48000, 16).pack() + struct.pack(">I", nb) + table.tobytes() + b"\0" * nb
+    bad = tmp_path / "crafted.lac"
+    bad.write_bytes(crafted)
+    res = _run(cli, "decode", str(bad), str(tmp_path / "o.wav"))
+    assert res.returncode == 1 and "decoded PCM allocation exceeds maximum" in res.stderr
+    assert not (tmp_path / "o.wav").exists()
+    res = _run(cli, "decode", str(bad), str(tmp_path / "o.wav"), "--allow-large")
+    assert res.returncode == 1 and "[decode-error] block=0 channel=primary" in res.stderr  # now it gets as far as the device

@@ -114,3 +114,30 @@ def test_serial_v2_stream(cd):
     assert np.array_equal(dl, l) and np.array_equal(dr, r)
     with pytest.raises(RuntimeError, match="trailing frame payload"):
         cd.decode(v2 + b"\0")
+
+
+def _shift_bits(data: bytes, k: int) -> bytes:
+    """`data` behind k junk bits (ones), MSB first, zero padded to a byte"""
+    v = (((1 << k) - 1) << (8 * len(data))) | int.from_bytes(data, "big")
+    total = k + 8 * len(data)
+    pad = (-total) % 8
+    return (v << pad).to_bytes((total + pad) // 8, "big")
+
+
+def test_block_decode_from_any_bit_position(cd):
+    """Block::Decoder::decode_into reads from wherever the reader stands (block/decoder.cpp:64); a reject that ran
+    out of data is told apart from a semantic one (the reference's reader is only then in its error state)."""
+    corpus = H.block_corpus()
+    for name in ("ar4_16384", "noise_n33", "zr_sweep_n96", "sparse_4096", "level_steps_16384"):
+        pcm = corpus[name]
+        blk = H.oracle().block_encode(pcm, True, True)
+        for k in (1, 3, 7, 13):
+            ok, out, bits, ran = cd.block_decode_at(_shift_bits(blk, k) + b"\xff" * 5, k, len(pcm))
+            assert ok and not ran and np.array_equal(out, pcm), (name, k)
+            assert (k + bits) % 8 == 0 and abs(bits - 8 * len(blk)) <= 7      # ends on a byte boundary of the buffer
+        ok, _, _, ran = cd.block_decode_at(blk[: len(blk) // 2], 0, len(pcm))
+        assert not ok and ran, name                      # truncated: data ran out
+    bad = bytearray(H.oracle().block_encode(corpus["noise_n33"], True, True))
+    bad[0] = 7                                            # predictor type 7: semantic reject, data is all there
+    ok, _, _, ran = cd.block_decode_at(bytes(bad), 0, 33)
+    assert not ok and not ran

@@ -277,6 +277,10 @@ except RuntimeError as e:
 big = np.zeros(need, dtype=np.uint8)
 n = cd.encode_into(iv, big, bb, 16, 2, 0)
 assert n == need and int(bb.sum()) == n
+cd.set_concurrency(1)  # one stream: the unsliced path, same bytes
+n1 = cd.encode_into(iv, big, bb, 16, 2, 0)
+assert n1 == n
+cd.set_concurrency(0)
 print("sliced ok")
 """
 
@@ -351,3 +355,48 @@ def restore_overflow_fuzz(cd, rounds, flips):
 
 def test_restore_overflow_verdicts(cd):
     assert restore_overflow_fuzz(cd, 24, 25) > 300
+
+
+def _shift_bits(data: bytes, k: int) -> bytes:
+    """`data` behind k junk bits (ones), MSB first, zero padded to a byte"""
+    v = (((1 << k) - 1) << (8 * len(data))) | int.from_bytes(data, "big")
+    total = k + 8 * len(data)
+    pad = (-total) % 8
+    return (v << pad).to_bytes((total + pad) // 8, "big")
+
+
+def test_block_decode_from_any_bit_position(cd):
+    """Block::Decoder::decode_into reads from wherever the reader stands (block/decoder.cpp:64); a reject that ran
+    out of data is told apart from a semantic one (the reference's reader is only then in its error state)."""
+    corpus = H.block_corpus()
+    for name in ("ar4_16384", "noise_n33", "zr_sweep_n96", "sparse_4096", "level_steps_16384"):
+        pcm = corpus[name]
+        blk = H.oracle().block_encode(pcm, True, True)
+        for k in (1, 3, 7, 13):
+            ok, out, bits, ran = cd.block_decode_at(_shift_bits(blk, k) + b"\xff" * 5, k, len(pcm))
+            assert ok and not ran and np.array_equal(out, pcm), (name, k)
+            assert (k + bits) % 8 == 0 and abs(bits - 8 * len(blk)) <= 7      # ends on a byte boundary of the buffer
+        ok, _, _, ran = cd.block_decode_at(blk[: len(blk) // 2], 0, len(pcm))
+        assert not ok and ran, name                      # truncated: data ran out
+    bad = bytearray(H.oracle().block_encode(corpus["noise_n33"], True, True))
+    bad[0] = 7                                            # predictor type 7: semantic reject, data is all there
+    ok, _, _, ran = cd.block_decode_at(bytes(bad), 0, 33)
+    assert not ok and not ran
+
+
+def test_concurrency_cap_same_bytes(cd):
+    """lacb_set_concurrency (the GPU path's --threads): 1 = one stream, nothing overlapped; bytes never change.
+    The input is long enough (2300 blocks) for the automatic plan to cut it into slices."""
+    l, r, pk = H.synth(2, 2300 * 16384 + 777, 24, want_packed=True)
+    ref = None
+    try:
+        for n in (1, 2, 0):
+            cd.set_concurrency(n)
+            payload, bb, sizes = cd.encode_blocks(None, None, 24, 1, packed=pk, channels=2)
+            (back,) = cd.decode_blocks(payload, sizes, bb, 24, 2, 1, packed=True)
+            assert np.array_equal(back, pk)
+            cur = (payload.tobytes(), bb.tobytes())
+            assert ref is None or cur == ref
+            ref = cur
+    finally:
+        cd.set_concurrency(0)

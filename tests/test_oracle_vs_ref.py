@@ -116,3 +116,31 @@ def test_config1_size_matches_survey():
     l, r = H.synth(1, 2_646_000, 16)
     b = H.ref().encode(l, r, 44100, 16, 2, threads=8)
     assert len(b) == 5_217_578
+
+
+def test_ranges_concatenate_to_whole_file():
+    """Blocks are independent: the reference's encodes of contiguous block ranges, assembled as
+    header + table + slabs in range order (src/codec/lac/encoder.cpp:445-465), are its encode of the whole file.
+    This is what lets tools/make_golden_large.py record config 4 (one 10 h file) range by range."""
+    import struct
+    frames = 37 * 16384 + 4321
+    l, r = H.synth_range(4, 0, frames, 24)
+    whole = H.ref().encode(l, r, 48000, 24, 2, threads=4)
+    nb = (frames + 16383) // 16384
+    for world in (2, 3, 8):
+        per = (nb + world - 1) // world
+        tables, slabs = [], []
+        for k in range(world):
+            b0, b1 = min(nb, k * per), min(nb, (k + 1) * per)
+            if b0 == b1:
+                continue
+            f0, f1 = b0 * 16384, min(frames, b1 * 16384)
+            rl, rr = H.synth_range(4, f0, f1 - f0, 24)  # the rank generates its own range of the one file
+            part = H.ref().encode(rl, rr, 48000, 24, 2, threads=2)
+            n = struct.unpack(">I", part[10:14])[0]
+            assert n == b1 - b0 and part[:10] == whole[:10]
+            tables.append(part[14:14 + 8 * n])
+            slabs.append(part[14 + 8 * n:])
+        assert whole == whole[:10] + struct.pack(">I", nb) + b"".join(tables) + b"".join(slabs)
+    # the C restatement agrees on the same file
+    assert H.oracle().encode(l, r, 48000, 24, 2) == whole

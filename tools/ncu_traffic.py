@@ -1,8 +1,10 @@
 """Extracts the DRAM traffic of the k_analyze launch from an `ncu --set full` report of
-`python bench.py` (default workload) and writes profiles/r1_roofline_traffic.json, which
-bench.py reports as roofline.traffic.
+`python bench.py` (default workload) and writes profiles/r2_roofline_traffic.json, which
+bench.py reports as roofline.traffic for as long as the kernel sources (SHA-256 of csrc/) are unchanged.
 usage: ncu_traffic.py gpurun_out/prof_an_full.ncu-rep frames_per_gpu"""
 import csv, io, json, subprocess, sys
+sys.path.insert(0, ".")
+from bench import kernel_src_sha
 rep, frames = sys.argv[1], int(sys.argv[2])
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
@@ -22,5 +24,6 @@ for r in rows[2:]:
     rec["dram_bytes_per_launch"] = rec["dram_bytes_read"] + rec["dram_bytes_write"]
     if best is None or rec["duration_ms_under_ncu"] > best["duration_ms_under_ncu"]:
         best = rec  # the full-size launch (the e2e leg launches smaller ones)
-json.dump(best, open("profiles/r1_roofline_traffic.json", "w"), indent=1)
+best["kernel_src_sha256"] = kernel_src_sha()
+json.dump(best, open("profiles/r2_roofline_traffic.json", "w"), indent=1)
 print(best)
