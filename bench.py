@@ -555,10 +555,33 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t0
 
+    # bare-copy ceiling of the e2e leg: the same page-locked buffers and the same bytes per step (PCM in, payload
+    # out, payload in, PCM out) with no kernel in between, all ranks at once -- what the host's PCIe / memory
+    # fabric alone allows; e2e is reported as a fraction of it
+    copy_wall = 0.0
+    if e2e_steps:
+        d_tmp = cd.dev_malloc(pcm_bytes)
+        lac_n = int(lac_e2e)
+
+        def copy_step():
+            cd.h2d(d_tmp, h_in)
+            cd.d2h_to(h_payload.ctypes.data, d_tmp, lac_n)
+            cd.h2d(d_tmp, h_payload[:lac_n])
+            cd.d2h_to(h_out.ctypes.data, d_tmp, pcm_bytes)
+
+        copy_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copy_step()
+        barrier()
+        copy_wall = time.perf_counter() - t0
+        cd.dev_free(d_tmp)
+
     if dist:
-        t = torch.tensor([wall, e2e_wall], dtype=torch.float64, device="cuda")
+        t = torch.tensor([wall, e2e_wall, copy_wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        wall, e2e_wall = float(t[0]), float(t[1])
+        wall, e2e_wall, copy_wall = float(t[0]), float(t[1]), float(t[2])
 
     c4 = None
     if args.c4 == "on" or (args.c4 == "auto" and world > 1):
@@ -610,7 +633,11 @@ def main():
                                 "frac": (pcm_bytes + lac) / parse_s / 1e9 / peak},
             "e2e": None if not e2e_steps else {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": pcm_bytes + lac_e2e, "d2h_bytes_per_step": lac_e2e + pcm_bytes,
-                    "steps": e2e_steps, "contexts": nctx},
+                    "steps": e2e_steps, "contexts": nctx,
+                    "copy_ceiling": pcm_bytes * world * e2e_steps / copy_wall / 1e9,
+                    "frac_of_copy_ceiling": copy_wall / e2e_wall,
+                    "copy_ceiling_note": "same pinned buffers and bytes per step (H2D PCM, D2H payload, H2D payload, D2H PCM), "
+                                         "no kernels, serial copies on one stream per rank, all ranks at once"},
             # per step: k_deinterleave, k_plan_fixed, k_build_jobs, k_autocorr, k_levinson, k_analyze,
             # k_finalize_blocks, k_emit (encode) + k_parse_blocks, k_restore_order, k_restore_blocks,
             # k_merge_restore_errors, k_finish_pcm (decode)

@@ -526,6 +526,49 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     __syncthreads();
 
     // partition search, block/encoder.cpp:486-545
+    const bool fused = (NT >= 64) && n == (uint32_t)(NT * E) && max_p >= 1u;
+    if (fused) {
+      // full blocks: every level in one sweep (levels_fused), then every segment's mode choice, then the levels' totals
+      constexpr uint32_t STR = ASmem<NT, E>::MAXSEG + 1u;
+      levels_fused<NT, E>(sm, pr, n, max_p);
+      const u64* Fa = sm.FbAll();
+      u64* SelBits = sm.SelBits();
+      for (uint32_t sid = 1u + tid; sid < (2u << max_p) - 1u; sid += NT) {
+        const u64 rice = Fa[sid], zr = Fa[STR + sid], bin = Fa[2u * STR + sid];
+        const bool hr = (mi->hasrun_all[sid >> 5] >> (sid & 31u)) & 1u;
+        const uint32_t kk = sm.SegK()[sid];
+        const u64 sbits = sm.SegStat()[sid];
+        uint32_t mode = MODE_RICE, k = kk & 0xFFu;
+        u64 bits = rice;
+        if (cfg.zero_run && hr && zr < bits) { mode = MODE_ZR; bits = zr; }
+        if (bin < bits) { mode = MODE_BIN; bits = bin; }
+        if (sbits < bits || sbits <= bits + bits / 20ull) { mode = MODE_STATIC; k = kk >> 8; bits = sbits; }  // :518, :190-192
+        sm.SelMK()[sid] = (uint8_t)((mode << 5) | k);
+        SelBits[sid] = bits;
+      }
+      __syncthreads();
+      const uint32_t warp = tid >> 5;
+      if (warp >= 1u && warp <= max_p) {  // warp p adds up level p
+        const uint32_t cnt = 1u << warp;
+        u64 part_sum = 0ull;
+        for (uint32_t s = tid & 31u; s < cnt; s += 32u) part_sum += SelBits[cnt - 1u + s];
+        const u64 sum_bits = warp_sum_u64(part_sum);
+        u64 total = sum_bits + 8ull + 7ull * cnt;
+        total += (8ull - (total & 7ull)) & 7ull;
+        if ((tid & 31u) == 0u) mi->lvl_total[warp] = total;
+      }
+      __syncthreads();
+      for (uint32_t p = 1u; p <= max_p; ++p) {
+        const u64 total = mi->lvl_total[p];
+        const u64 margin = best_total / 20ull;
+        if (total < best_total || (total <= best_total + margin && best_p == 0u) ||
+            (total == best_total && p < best_p)) {  // :538-540
+          best_total = total;
+          best_p = p;
+        }
+      }
+      LACB_PH(16);
+    } else
     for (uint32_t p = 1u; p <= max_p; ++p) {
       const bool sums = cost_pass<NT, E, false>(sm, pr, n, p, 0u) != 0u;  // Fb: per-segment sums or prefixes
       const uint32_t cnt = 1u << p;
@@ -569,7 +612,15 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
                               : best.order;  // block/encoder.cpp:421-423
     const uint32_t nparts = 1u << best_p;
     u64 tok_bits = 0ull;
-    {
+    if (fused && best_p >= 1u) {
+      // full block, partitioned: the register walk of the level sweep, no K plane, no barrier
+      chunk_walk_stateless<NT, E, true>(sm, pr, n, best_p,
+                                        [&](uint32_t u, uint32_t k, bool is_zero, uint32_t closes, bool long_run, uint32_t m) {
+                                          bool emit;
+                                          const Token t = make_token(m >> 5, m & 31u, u, k, is_zero, closes, long_run, &emit);
+                                          if (emit) tok_bits += (u64)t.hlen + t.q + t.tlen;
+                                        });
+    } else {
       const SegGeom sg = seg_geom<E>(g0, n, best_p);
       const uint8_t* mk = sm.SelMK();
       const uint32_t mkA = mk[sg.sidA], mkB = (sg.bnd != 0xFFFFFFFFu) ? mk[sg.sidA + 1u] : 0u;

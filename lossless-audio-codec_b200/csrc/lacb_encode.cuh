@@ -77,6 +77,8 @@ struct AMisc {
   uint32_t lb;  // lower bound of the candidate's cost (see prepare)
   uint32_t hq_n, hq_kb_n;  // entries in the hard-chunk queue (bias pairs / base-k pairs)
   uint32_t hasrun_bits[8];
+  uint32_t hasrun_all[16];  // fused levels: has-run bit of every segment, indexed by table id
+  u64 lvl_total[9];         // fused levels: byte-rounded total of every level
 };
 
 template <int NT, int E>
@@ -110,6 +112,10 @@ struct ASmem {
   __device__ uint32_t* U() const { return reinterpret_cast<uint32_t*>(base + oU); }
   __device__ u64* Pthr() const { return reinterpret_cast<u64*>(base + oPthr); }
   __device__ PlaneCounts* Cpre() const { return reinterpret_cast<PlaneCounts*>(base + oCpre); }
+  // per-segment cost sums of all levels (3 x (MAXSEG + 1) u64): aliases Cpre, which is dead once the segment
+  // tables are built
+  __device__ u64* FbAll() const { return reinterpret_cast<u64*>(base + oCpre); }
+  static_assert(3u * (MAXSEG + 1u) * 8u <= (size_t)(NT + 1) * 32u || NT < 64, "FbAll must fit inside Cpre");
   __device__ uint32_t* Flg() const { return reinterpret_cast<uint32_t*>(base + oFlg); }
   __device__ uint32_t* Kpl() const { return reinterpret_cast<uint32_t*>(base + oKpub); }  // k per sample, 1 byte each
   __device__ u64* Scr() const { return reinterpret_cast<u64*>(base + oScr); }
@@ -1257,6 +1263,272 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     LACB_PH(15);
     return 0u;
   }
+}
+
+// ---------------------------------------------------------------------------
+// All partition levels of a FULL block in one sweep (block/encoder.cpp:486-545).
+//
+// The stateless model restarts at every segment start, so the k series and the costs of a chunk depend on the
+// level only through (a) the start of the segment the chunk lies in and (b) whether the chunk is the last one of
+// its segment (zero runs are clipped at the boundary).  Segment starts nest: going one level deeper, a chunk in a
+// left child keeps its start, and once a chunk is last-in-segment it stays so.  A thread therefore walks the
+// levels with its samples in registers and re-evaluates its chunk only when (start, last, initial k) changes -- 5.5 of the 8
+// levels on average instead of 8, each without the K plane, the hard-chunk queue or any block barrier (the k of the
+// sample before the chunk is one more closed-form evaluation instead of a neighbour's K word).  The per-segment sums
+// of every level are accumulated side by side (FbAll, aliasing the plane-count prefix that is dead by now) and the
+// level choice is made after a single barrier.
+template <int NT, int E, bool ZR, typename F>
+__device__ __forceinline__ void walk_regs(const uint32_t (&u)[E], const uint32_t (&kpk)[E / 4], uint32_t kprev,
+                                          uint32_t zm, uint32_t z, F&& f) {
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    const uint32_t k = (j == 0) ? kprev : ((kpk[(j - 1) >> 2] >> (8 * ((j - 1) & 3))) & 0xFFu);
+    if (ZR) {
+      const bool is_zero = (zm >> j) & 1u;
+      z = is_zero ? z + 1u : 0u;
+      const uint32_t fwd = (uint32_t)__ffs((int)~(zm >> (j + 1))) - 1u;
+      const bool long_run = is_zero && (z + fwd >= kZrMinRun);
+      const uint32_t closes = (long_run && fwd == 0u) ? z : 0u;
+      f(j, u[j], k, is_zero, closes, long_run);
+    } else {
+      f(j, u[j], k, u[j] == 0u, 0u, false);
+    }
+  }
+}
+
+// base k of a chunk that lies inside one segment starting at a0 (prefix of u there: Pa), samples in registers
+template <int NT, int E>
+__device__ __forceinline__ void k_chunk_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, const uint32_t (&u)[E],
+                                                  uint32_t a0, u64 Pa, uint32_t (&kpk)[E / 4]) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const u64 S = sm.Pthr()[tid + 1u] - pr.Pex;
+  const uint32_t c_first = g0 - a0 + 1u, c_last = c_first + (uint32_t)E - 1u;
+  const u64 rel = pr.Pex - Pa;
+  const u64 N_first = rel + u[0] + (c_first >> 1), N_last = rel + S + (c_last >> 1);
+  const uint32_t kb0 = kbase_clz(N_first, c_first);
+  bool uniform;
+  if (kb0 == 0u) {
+    uniform = N_last < 2ull * c_first;
+  } else {
+    const u64 lo = (1ull << (kb0 - 1u)) + 1ull, hi = (1ull << kb0) + 1ull;
+    uniform = (N_first >= lo * c_last) && (kb0 == 31u || N_last < hi * c_first);
+  }
+  if (uniform) {
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = kb0 * 0x01010101u;
+    return;
+  }
+#pragma unroll
+  for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = 0u;
+  if (N_last < 0x80000000ull) {
+    uint32_t N32 = (uint32_t)rel;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      N32 += u[j];
+      const uint32_t c = c_first + (uint32_t)j;
+      kpk[j >> 2] |= kbase_clz32(N32 + (c >> 1), c) << (8 * (j & 3));
+    }
+    return;
+  }
+  u64 N = rel;
+#pragma unroll
+  for (int j = 0; j < E; ++j) {
+    N += u[j];
+    const uint32_t c = c_first + (uint32_t)j;
+    kpk[j >> 2] |= kbase_clz(N + (c >> 1), c) << (8 * (j & 3));
+  }
+}
+
+// k series of the chunk in registers plus the k in force for its first sample: the segment's initial k at a
+// segment start, else the model after the sample before the chunk (one more closed-form evaluation)
+template <int NT, int E>
+__device__ __forceinline__ void chunk_k_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, const uint32_t (&u)[E],
+                                                  uint32_t sid, uint32_t a0, uint32_t (&kpk)[E / 4], uint32_t& kprev) {
+  const uint32_t g0 = threadIdx.x * E;
+  const u64 Pa = sm.SegP()[sid];
+  k_chunk_stateless<NT, E>(sm, pr, u, a0, Pa, kpk);
+  if (g0 == a0) {
+    kprev = sm.SegK()[sid] & 0xFFu;
+  } else {
+    const uint32_t c = g0 - a0;
+    kprev = kbase_clz(pr.Pex - Pa + (c >> 1), c);
+  }
+}
+
+// Token walk of the thread's chunk at partition level p >= 1 of a FULL block, k series in registers:
+//   f(u, k, is_zero, closes, long_run, mk)   with mk = (mode << 5) | k of the chunk's segment (SelMK)
+// `kinit_from_mk`: the emitter has no SegK table; the initial k of an adaptive segment is the k field of its mk.
+template <int NT, int E, bool KINIT_FROM_MK, typename F>
+__device__ __forceinline__ void chunk_walk_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
+                                                     uint32_t p, F&& f) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t base = n >> p, cnt = 1u << p, per_seg = (uint32_t)NT >> p;
+  const uint32_t s0 = tid / per_seg, a0 = s0 * base, sid = cnt - 1u + s0;
+  const bool last = (s0 + 1u < cnt) && (g0 + (uint32_t)E == a0 + base);
+  uint32_t u[E];
+  load_u<NT, E>(sm, u);
+  const uint32_t mk = sm.SelMK()[sid];
+  uint32_t kpk[E / 4], kprev;
+  if ((mk >> 5) == MODE_STATIC) {  // the adaptive series is not used: every sample takes the segment's static k
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) kpk[c4] = 0u;
+    kprev = 0u;
+  } else {
+    chunk_k_stateless<NT, E>(sm, pr, u, sid, a0, kpk, kprev);
+    if (KINIT_FROM_MK && g0 == a0) kprev = mk & 31u;
+  }
+  constexpr uint32_t kAll = (1u << E) - 1u;
+  if (pr.any4) {
+    const uint32_t zm_all = zero_lookahead(sm, pr, n);
+    const uint32_t byscan = g0 - 1u - (uint32_t)pr.lnz_ex, byseg = g0 - a0;
+    walk_regs<NT, E, true>(u, kpk, kprev, last ? (zm_all & kAll) : zm_all, byscan < byseg ? byscan : byseg,
+                           [&](int, uint32_t uu, uint32_t k, bool is_zero, uint32_t closes, bool long_run) {
+                             f(uu, k, is_zero, closes, long_run, mk);
+                           });
+  } else {
+    walk_regs<NT, E, false>(u, kpk, kprev, 0u, 0u,
+                            [&](int, uint32_t uu, uint32_t k, bool is_zero, uint32_t closes, bool long_run) {
+                              f(uu, k, is_zero, closes, long_run, mk);
+                            });
+  }
+}
+
+// costs of one chunk of a full block under the stateless model of the segment [a0, ...) -- the three tiers of
+// cost_pass with the k series in registers.  `last` = the chunk ends where its segment ends.
+template <int NT, int E>
+__device__ __forceinline__ void chunk_costs_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr,
+                                                      const uint32_t (&u)[E], uint32_t zm_all, uint32_t sid, uint32_t a0,
+                                                      bool last, u64& rice, u64& zr, u64& bin, uint32_t& run) {
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  uint32_t kpk[E / 4], kprev;
+  chunk_k_stateless<NT, E>(sm, pr, u, sid, a0, kpk, kprev);
+  run = 0u;
+  bool plain = !(pr.cls & 1u) && (pr.cls >> 8) <= 24u;
+  if (plain) {
+    uint32_t acc = 0u, qor = 0u, ksum = 0u, kp = kprev;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const uint32_t k = kp;
+      kp = (kpk[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+      const uint32_t q = (k >= 31u) ? 0u : (u[j] >> k);
+      qor |= q;
+      acc += q;
+      ksum += k;
+    }
+    if (qor < 8u) {
+      rice = (u64)(acc + ksum + (uint32_t)E);
+      zr = bin = rice + 2ull * (uint32_t)E;
+      return;
+    }
+  }
+  constexpr uint32_t kAll = (1u << E) - 1u;
+  if (pr.any4 && (pr.zmask & kAll) == kAll && !last && (zm_all >> E) == 0xFu) {  // silent chunk inside a longer run
+    uint32_t ksum = kprev;
+#pragma unroll
+    for (int c4 = 0; c4 < E / 4; ++c4) {
+      const uint32_t kw = kpk[c4];
+      ksum += (kw & 0xFFu) + ((kw >> 8) & 0xFFu) + ((kw >> 16) & 0xFFu) + ((kw >> 24) & 0xFFu);
+    }
+    ksum -= kpk[E / 4 - 1] >> 24;
+    rice = (u64)(ksum + (uint32_t)E);
+    bin = 2ull * (uint32_t)E;
+    zr = 0ull;
+    return;
+  }
+  u64 r = 0, z = 0, b = 0;
+  uint32_t rn = 0u;
+  auto body = [&](int, uint32_t uu, uint32_t k, bool is_zero, uint32_t closes, bool long_run) {
+    const u64 rc = rice_cost(uu, k);
+    u64 bc, zc;
+    if (is_zero) bc = 2ull;
+    else if (uu <= 4u) bc = 3ull;
+    else bc = 2ull + rc;
+    if (!pr.any4) {
+      zc = 0ull;
+    } else if (!is_zero) {
+      const uint32_t esc = 1u << (k + 3u < 24u ? k + 3u : 24u);
+      zc = 2ull + ((uu > esc) ? 32ull : rc);
+    } else if (long_run) {
+      zc = closes ? 2ull + rice_cost(closes - kZrMinRun, kZrRunK) : 0ull;
+    } else {
+      zc = 2ull + rc;
+    }
+    r += rc;
+    z += zc;
+    b += bc;
+    rn |= (closes != 0u);
+  };
+  if (pr.any4) {
+    // zeros right before the chunk inside the segment; look-ahead clipped at the segment end
+    const uint32_t byscan = g0 - 1u - (uint32_t)pr.lnz_ex, byseg = g0 - a0;
+    const uint32_t z0 = byscan < byseg ? byscan : byseg;
+    walk_regs<NT, E, true>(u, kpk, kprev, last ? (zm_all & kAll) : zm_all, z0, body);
+  } else {
+    walk_regs<NT, E, false>(u, kpk, kprev, 0u, 0u, body);
+  }
+  rice = r;
+  zr = z;
+  bin = b;
+  run = rn;
+}
+
+// Sums of all levels 1..max_p into FbAll[mode * (MAXSEG + 1) + sid] and the has-run bits of every segment into
+// AMisc::hasrun_all.  Full blocks only (n == NT * E).  Ends with a barrier.
+template <int NT, int E>
+__device__ __forceinline__ void levels_fused(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t max_p) {
+  constexpr uint32_t STR = ASmem<NT, E>::MAXSEG + 1u;
+  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  AMisc* mi = sm.Misc();
+  u64* Fa = sm.FbAll();
+  for (uint32_t i = tid; i < 3u * STR; i += NT) Fa[i] = 0ull;
+  if (tid < 16u) mi->hasrun_all[tid] = 0u;
+  __syncthreads();
+  uint32_t u[E];
+  load_u<NT, E>(sm, u);
+  const uint32_t zm_all = pr.any4 ? zero_lookahead(sm, pr, n) : 0u;
+  uint32_t prevA = 0xFFFFFFFFu, prevKin = 0xFFFFFFFFu;
+  bool prevLast = false;
+  u64 rice = 0, zr = 0, bin = 0;
+  uint32_t run = 0u;
+  for (uint32_t p = 1u; p <= max_p; ++p) {
+    const uint32_t base = n >> p, cnt = 1u << p;
+    const uint32_t per_seg = (uint32_t)NT >> p;  // threads per segment: 512 ... 4
+    const uint32_t s0 = tid / per_seg;
+    const uint32_t a0 = s0 * base, sid = cnt - 1u + s0;
+    const bool last = (s0 + 1u < cnt) && (g0 + (uint32_t)E == a0 + base);  // a boundary follows the chunk
+    // a chunk that opens its segment also depends on the segment's initial k, which looks at the first
+    // min(256, length) samples and so changes with the level once segments are shorter than that
+    const uint32_t kin = (g0 == a0) ? (uint32_t)(sm.SegK()[sid] & 0xFFu) : 0xFFFFFFFFu;
+    if (a0 != prevA || last != prevLast || kin != prevKin) {
+      chunk_costs_stateless<NT, E>(sm, pr, u, zm_all, sid, a0, last, rice, zr, bin, run);
+      prevA = a0;
+      prevLast = last;
+      prevKin = kin;
+    }
+    u64 a = rice, b = zr, c = bin;
+    uint32_t rn = run;
+    if (per_seg >= 32u) {
+      a = warp_sum_u64(a);
+      b = warp_sum_u64(b);
+      c = warp_sum_u64(c);
+      rn = __reduce_or_sync(kFull, rn);
+    } else {
+      for (uint32_t d = per_seg >> 1; d > 0u; d >>= 1) {  // groups of 16 / 8 / 4 lanes
+        a += __shfl_xor_sync(kFull, a, (int)d);
+        b += __shfl_xor_sync(kFull, b, (int)d);
+        c += __shfl_xor_sync(kFull, c, (int)d);
+        rn |= __shfl_xor_sync(kFull, rn, (int)d);
+      }
+    }
+    const uint32_t lead = per_seg >= 32u ? 31u : per_seg - 1u;
+    if ((tid & lead) == 0u) {
+      atomicAdd(&Fa[sid], a);
+      if (pr.any4) atomicAdd(&Fa[STR + sid], b);
+      atomicAdd(&Fa[2u * STR + sid], c);
+      if (rn) atomicOr(&mi->hasrun_all[sid >> 5], 1u << (sid & 31u));
+    }
+  }
+  __syncthreads();
 }
 
 // Exact emitted bit count of the thread's samples for the final decision.

@@ -141,3 +141,14 @@ def test_block_decode_from_any_bit_position(cd):
     bad[0] = 7                                            # predictor type 7: semantic reject, data is all there
     ok, _, _, ran = cd.block_decode_at(bytes(bad), 0, 33)
     assert not ok and not ran
+
+
+def test_partition_levels_share_segment_starts(cd):
+    """Fused partition-level sweep: a chunk keeps its costs from level to level only while (segment start, last-in-
+    segment, initial k) are unchanged.  Triangle-section blocks of config 1 (two verbatim warm-up samples, then small
+    residuals) have an initial k that changes once segments get shorter than 256 samples: the case that pins the key."""
+    l, r = H.synth(1, 46 * 16384, 16)
+    m = ((l.astype(np.int64) + r) >> 1).astype(np.int32)
+    for b in (10, 44, 45):
+        x = m[b * 16384:(b + 1) * 16384]
+        assert cd.block_encode(x, True, True) == H.oracle().block_encode(x, True, True), b
