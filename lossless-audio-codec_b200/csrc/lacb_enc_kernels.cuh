@@ -380,18 +380,95 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     job_desc<PROBE>(src, slot, jd);
     const uint32_t n = jd.n;
     LACB_PH_INIT(PROBE ? -1 : 0);
+    if (tid < 11u) mi->cand_lb[tid] = 0u;  // ordered before the pre-pass by the barrier of the vote below
     // block-uniform: some sample needs more than 26 magnitude bits (never true for 16 / 24-bit audio);
     // only then can an LPC residual leave int32 (lpc.cpp:38-61) and the fallback orders matter
     const bool xbig = __syncthreads_or((int)((load_block<NT, E>(sm, src, jd.kind, jd.start, n) >> 26) != 0u)) != 0;
     LACB_PH(0);
     const uint32_t max_valid = n > 1u ? (n - 1u < 32u ? n - 1u : 32u) : 0u;
     const LpcQ* lq = lpcq + slot;
-    if (!PROBE && tid < 11u) recs[slot].cand_lo[tid] = 0xFFFFFFFFu;
 
-    if (tid == 0u) mi->best.have = 0u;  // ordered before its first use by the barriers of the first candidate
+    // ---- which candidates exist: fixed 0..4, FIR, LPC 4,6,8,10,12 (block/encoder.cpp:362-407), and the taps an LPC
+    // candidate's residual uses (compute_residual_q15's first attempt, lpc.cpp:188-229)
+    auto cand_taps = [&](uint32_t ci) -> uint32_t {  // 0 = candidate does not exist; fixed / FIR report 1
+      if (ci <= 5u) return 1u;
+      const uint32_t c = ci - 6u, co = 4u + 2u * c;
+      if (co > max_valid) return 0u;
+      const uint32_t used = (uint32_t)lq->used[c];  // 0: unstable, block/encoder.cpp:394-396
+      return used < co ? used : co;
+    };
+
+    // ---- pre-pass: an exact lower bound of every candidate's cost, before anything expensive.
+    // Whatever the mode and k, a sample costs at least bit_width(u) + 1 bits (32 for u >= 2^31, where the k = 31
+    // estimate drops the quotient; 3 for u = 4 as a bin code; 0 for a zero inside a run), so the sum over the
+    // residual bounds min(rice, static, zero-run, bin) from below.  The candidates are then evaluated in ascending
+    // order of their bound: the likely winner comes first, and as soon as a bound exceeds the best exact cost so
+    // far that candidate and all later ones cannot win or tie (block/encoder.cpp:352-359) and are never evaluated --
+    // they pay for this pass only, not for the residual / scan / bit-plane counts of a full evaluation.
+    // Skipped when an LPC residual could leave int32 (|x| >= 2^26, never for 16 / 24-bit audio): the fallback
+    // orders then need block-wide votes, and every candidate is simply evaluated in index order.
+    if (!xbig) {
+      int32_t x[E + 12];
+      load_items<NT, E>(sm, x);
+      auto bound = [&](const int32_t (&r)[E]) -> uint32_t {
+        uint32_t a = 0u, z = 0u, n4 = 0u;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+          const uint32_t uu = zz32(r[j]);  // residuals past the block end are 0
+          const uint32_t lz = (uint32_t)__clz((int)uu);
+          a += lz ? lz : 1u;  // u >= 2^31: 32 bits, not 33
+          z += lz >> 5;       // zeros (and missing samples) cost nothing
+          n4 += uu == 4u ? 1u : 0u;
+        }
+        return 33u * (uint32_t)E - a - z - n4;
+      };
+      auto publish = [&](uint32_t ci, uint32_t lbt) {
+        const uint32_t t = warp_sum_u32(lbt);
+        if ((tid & 31u) == 0u && t) atomicAdd(&mi->cand_lb[ci], t);
+      };
+      {
+        int32_t r[E];
+        residual_fixed<E>(x, g0, n, 0, r); publish(0u, bound(r));
+        residual_fixed<E>(x, g0, n, 1, r); publish(1u, bound(r));
+        residual_fixed<E>(x, g0, n, 2, r); publish(2u, bound(r));
+        residual_fixed<E>(x, g0, n, 3, r); publish(3u, bound(r));
+        residual_fixed<E>(x, g0, n, 4, r); publish(4u, bound(r));
+        residual_fir<E>(x, g0, n, r); publish(5u, bound(r));
+#pragma unroll 1
+        for (uint32_t ci = 6u; ci < 11u; ++ci) {
+          const uint32_t taps = cand_taps(ci);
+          if (taps == 0u) continue;
+          residual_lpc<E, false>(x, g0, n, lq->coef[ci - 6u], (int)taps, r);
+          publish(ci, bound(r));
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < 11u) {
+      // rank of candidate `tid` among the existing ones by (bound, index); without the pre-pass all bounds are 0
+      const uint32_t mine = mi->cand_lb[tid];
+      const bool exists = cand_taps(tid) != 0u;
+      uint32_t rank = 0u, total = 0u;
+      for (uint32_t cj = 0; cj < 11u; ++cj) {
+        if (cand_taps(cj) == 0u) continue;
+        ++total;
+        const uint32_t other = mi->cand_lb[cj];
+        if (other < mine || (other == mine && cj < tid)) ++rank;
+      }
+      if (exists) mi->cand_order[rank] = (uint8_t)tid;
+      if (tid == 0u) mi->cand_n = total;
+      if (!PROBE) recs[slot].cand_lo[tid] = exists ? 0xFFFFFFFEu : 0xFFFFFFFFu;  // overwritten when evaluated
+    }
+    if (tid == 0u) mi->best.have = 0u;
     if (tid == 0u) mi->hq_kb_n = 0u;
-    // candidate order: fixed 0..4, FIR, LPC 4,6,8,10,12 (block/encoder.cpp:362-407)
-    for (uint32_t ci = 0; ci < 11u; ++ci) {
+    __syncthreads();
+    const uint32_t n_cand = mi->cand_n;
+    bool have_best = false;
+    u64 best_bits = 0ull;
+    uint32_t best_ci = 0u;
+    for (uint32_t idx = 0; idx < n_cand; ++idx) {
+      const uint32_t ci = mi->cand_order[idx];
+      if (have_best && (u64)mi->cand_lb[ci] > best_bits) break;  // this one and all later ones are out
       int32_t r[E];
       uint32_t type, order, taps = 0u;
       {
@@ -399,71 +476,72 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         // 28 registers across the whole search
         int32_t x[E + 12];
         load_items<NT, E>(sm, x);
-      if (ci <= 4u) {
-        type = PRED_FIXED;
-        order = ci;
-        residual_fixed<E>(x, g0, n, (int)ci, r);
-      } else if (ci == 5u) {
-        type = PRED_FIR;
-        order = 2u;
-        residual_fir<E>(x, g0, n, r);
-      } else {
-        const uint32_t c = ci - 6u, co = 4u + 2u * c;
-        if (co > max_valid) continue;
-        const uint32_t used = (uint32_t)lq->used[c];
-        if (used == 0u) continue;  // block/encoder.cpp:394-396
-        type = PRED_LPC;
-        order = co;
-        // compute_residual_q15 attempts (lpc.cpp:188-229): used, then {12,10,8,6,4} below it
-        uint32_t attempt = used < co ? used : co;
-        if (!xbig) {
-          residual_lpc<E, false>(x, g0, n, lq->coef[c], (int)attempt, r);
-          taps = attempt;
-          attempt = 0u;
-        }
-        while (attempt > 0u) {
-          const bool ovf = residual_lpc<E, true>(x, g0, n, lq->coef[c], (int)attempt, r);
-          if (!__syncthreads_or((int)ovf)) {
+        if (ci <= 4u) {
+          type = PRED_FIXED;
+          order = ci;
+          residual_fixed<E>(x, g0, n, (int)ci, r);
+        } else if (ci == 5u) {
+          type = PRED_FIR;
+          order = 2u;
+          residual_fir<E>(x, g0, n, r);
+        } else {
+          const uint32_t c = ci - 6u, co = 4u + 2u * c;
+          type = PRED_LPC;
+          order = co;
+          // compute_residual_q15 attempts (lpc.cpp:188-229): used, then {12,10,8,6,4} below it
+          uint32_t attempt = cand_taps(ci);
+          if (!xbig) {
+            residual_lpc<E, false>(x, g0, n, lq->coef[c], (int)attempt, r);
             taps = attempt;
-            break;
+            attempt = 0u;
           }
-          uint32_t next = 0u;
-          for (uint32_t fo = 12u; fo >= 4u; fo -= 2u)
-            if (fo < attempt && fo <= co) {
-              next = fo;
+          while (attempt > 0u) {
+            const bool ovf = residual_lpc<E, true>(x, g0, n, lq->coef[c], (int)attempt, r);
+            if (!__syncthreads_or((int)ovf)) {
+              taps = attempt;
               break;
             }
-          attempt = next;
+            uint32_t next = 0u;
+            for (uint32_t fo = 12u; fo >= 4u; fo -= 2u)
+              if (fo < attempt && fo <= co) {
+                next = fo;
+                break;
+              }
+            attempt = next;
+          }
+          if (taps == 0u) continue;  // block/encoder.cpp:402-404
         }
-        if (taps == 0u) continue;  // block/encoder.cpp:402-404
-      }
       }
       Prep<NT, E> pr;
       LACB_PH(1);
       prepare<NT, E, false>(sm, r, n, pr);
-      if (mi->best.have && (u64)mi->lb > mi->best.best) {
-        // cannot beat (or tie) the best candidate so far: skip its adaptive-k evaluation
-        if (!PROBE && tid == 0u) recs[slot].cand_lo[ci] = 0xFFFFFFFEu;
-        __syncthreads();  // everyone has read lb / best before the next candidate resets them
-        continue;
-      }
       // (the block's initial / static k are evaluated inside the pass, see block_static_k)
       const uint32_t has_run = cost_pass<NT, E, true>(sm, pr, n, 0u, 0u);
-      if (tid == (uint32_t)(NT - 32)) {  // bookkeeping on the last warp: the first warps are the loaded ones
+      {
+        // Every thread scores the candidate from the block totals (published by the barrier that ends the pass; the
+        // next writes to them lie behind the barriers of the next evaluation) and keeps the running best in
+        // registers, so the loop-exit test above is block-uniform without another barrier.  One lane keeps the
+        // full record of the best candidate in shared memory for the partition search.
         const u64 stat = mi->stat_bits;
-        const uint32_t k_init = mi->k_init, k_stat = mi->k_stat;
         const u64 rice = mi->tot_rice, bin = mi->tot_bin;
         const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
         const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
         const u64 bb = m1 < m2 ? m1 : m2;
-        if (!PROBE) recs[slot].cand_lo[ci] = (uint32_t)bb;
-        BestCand& best = mi->best;
-        if (!best.have || bb < best.best || (bb == best.best && type < best.type)) {  // :352-359
-          best.have = 1u;
-          best.rice = rice; best.zr = zr; best.bin = bin; best.stat = stat; best.best = bb;
-          best.type = type; best.order = order; best.taps = taps; best.ci = ci;
-          best.k_init = k_init; best.k_stat = k_stat; best.has_run = has_run;
+        // strictly fewer bits wins; on a tie the lower predictor type, then the earlier candidate (:352-359) --
+        // the type never decreases with the index, so that is the lower index whatever the evaluation order
+        if (!have_best || bb < best_bits || (bb == best_bits && ci < best_ci)) {
+          have_best = true;
+          best_bits = bb;
+          best_ci = ci;
+          if (tid == (uint32_t)(NT - 32)) {  // the last warp: the first warps are the loaded ones
+            BestCand& best = mi->best;
+            best.have = 1u;
+            best.rice = rice; best.zr = zr; best.bin = bin; best.stat = stat; best.best = bb;
+            best.type = type; best.order = order; best.taps = taps; best.ci = ci;
+            best.k_init = mi->k_init; best.k_stat = mi->k_stat; best.has_run = has_run;
+          }
         }
+        if (!PROBE && tid == (uint32_t)(NT - 32)) recs[slot].cand_lo[ci] = (uint32_t)bb;
       }
     }
     LACB_PH(1);

@@ -74,7 +74,9 @@ struct AMisc {
   u64 tot_rice, tot_zr, tot_bin, u_total, p_first, stat_bits, red64;
   uint32_t cnt_tot[8], cnt_first[8];
   uint32_t k_init, k_stat;  // initial / static k of the candidate (block_static_k)
-  uint32_t lb;  // lower bound of the candidate's cost (see prepare)
+  uint32_t cand_lb[11];    // exact lower bound of every candidate's cost (pre-pass of k_analyze)
+  uint32_t cand_n;         // candidates that exist
+  uint8_t cand_order[12];  // evaluation order: ascending (bound, index)
   uint32_t hq_n, hq_kb_n;  // entries in the hard-chunk queue (bias pairs / base-k pairs)
   uint32_t hasrun_bits[8];
   uint32_t hasrun_all[16];  // fused levels: has-run bit of every segment, indexed by table id
@@ -331,7 +333,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   uint32_t u[E];
   u64 S = 0;
   int32_t lastnz = -1;
-  uint32_t zmask = 0, umin = 0xFFFFFFFFu, uor = 0u, clzsum = 0u, n4 = 0u;
+  uint32_t zmask = 0, umin = 0xFFFFFFFFu, uor = 0u;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
     const bool in = g0 + j < n;
@@ -339,31 +341,12 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     u[j] = uu;
     S += uu;
     uor |= uu;
-    if (!FULL && !LIGHT) {
-      clzsum += (uint32_t)__clz((int)uu);
-      n4 += uu == 4u ? 1u : 0u;
-    }
     if (in && uu < umin) umin = uu;
     if (uu) lastnz = (int32_t)(g0 + j);
     if (in && uu == 0u) zmask |= 1u << j;
   }
   pr.zmask = zmask;
   pr.cls = (umin <= 4u ? 1u : 0u) | ((32u - (uint32_t)__clz((int)uor)) << 8);
-  // Lower bound of what this residual can cost under ANY of the four coding modes, per sample:
-  // a Rice code of u takes at least bit_width(u) + 1 bits whatever k is (32 when u >= 2^31, where
-  // the k = 31 estimate drops the quotient); the bin code of u = 4 takes 3; a zero inside a
-  // zero run can be free; zero-run escapes and tags only add.  Candidates whose bound already
-  // exceeds the best exact cost so far are dropped before the expensive adaptive-k passes.
-  uint32_t lbt = 0u;
-  if (!FULL && !LIGHT) {
-    const uint32_t inr = g0 >= n ? 0u : (n - g0 < (uint32_t)E ? n - g0 : (uint32_t)E);
-    lbt = 33u * (uint32_t)E - clzsum;                                // sum of bit_width(u) + 1, zeros counted as 1
-    lbt -= (uint32_t)__popc(zmask) + ((uint32_t)E - inr) + n4;       // zeros and missing samples: 0; u == 4: 3
-    if (uor >> 31) {
-#pragma unroll
-      for (int j = 0; j < E; ++j) lbt -= u[j] >> 31;
-    }
-  }
   uint4* U4 = reinterpret_cast<uint4*>(sm.U());
 #pragma unroll
   for (int c = 0; c < E / 4; ++c)
@@ -371,7 +354,6 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   if (!FULL && !LIGHT && tid < 8) {
     mi->cnt_tot[tid] = 0u;
     mi->cnt_first[tid] = 0u;
-    if (tid == 0) mi->lb = 0u;
   }
   uint32_t V[5] = {0u, 0u, 0u, 0u, 0u};
   if (!LIGHT) csa_count<E>(u, V);
@@ -392,20 +374,51 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   if (LIGHT) {
     // nothing to count
   } else if (FULL) {
+    // exclusive prefix of the eight packed plane-count words over the threads, all eight in one two-level
+    // scan (two barriers instead of sixteen); the per-warp totals go through the Fb area, idle at this point
     PlaneCounts* Cp = sm.Cpre();
+    constexpr int NW = (NT + 31) / 32;
+    const uint32_t lane = tid & 31u, wid = tid >> 5;
+    uint32_t inc[8];
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      uint32_t tot;
-      const uint32_t ex = block_excl_scan_u32<NT>(pc.w[w], reinterpret_cast<uint32_t*>(sm.Scr()), &tot);
-      Cp[tid].w[w] = ex;
-      if (tid == 0) Cp[NT].w[w] = tot;
+      inc[w] = pc.w[w];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, inc[w], d);
+        if (lane >= (uint32_t)d) inc[w] += y;
+      }
     }
+    uint32_t* wtot = reinterpret_cast<uint32_t*>(sm.Fb());  // [warp][8]
+    if (NW > 1) {
+      if (lane == 31u) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) wtot[wid * 8u + w] = inc[w];
+      }
+      __syncthreads();
+    }
+    PlaneCounts ex;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      uint32_t before = 0u, total = __shfl_sync(kFull, inc[w], 31);
+      if (NW > 1) {
+        uint32_t ws = lane < (uint32_t)NW ? wtot[lane * 8u + w] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t y = __shfl_up_sync(kFull, ws, d);
+          if (lane >= (uint32_t)d) ws += y;
+        }
+        const uint32_t wprev = __shfl_sync(kFull, ws, (int)((wid + 31u) & 31u));
+        before = wid ? wprev : 0u;
+        total = __shfl_sync(kFull, ws, NW - 1);
+      }
+      ex.w[w] = before + inc[w] - pc.w[w];
+      if (tid == 0) Cp[NT].w[w] = total;
+    }
+    Cp[tid] = ex;
+    __syncthreads();
   } else {
     const bool first = g0 < 256u;
-    {
-      const uint32_t t = warp_sum_u32(lbt);
-      if ((tid & 31u) == 0u && t) atomicAdd(&mi->lb, t);
-    }
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
       const uint32_t t = warp_sum_u32(pc.w[w]);
