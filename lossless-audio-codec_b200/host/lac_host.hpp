@@ -227,4 +227,7 @@ namespace lacb_host {
 int device_count();
 // resolves --devices / LAC_DEVICES: 0 or unset => 1
 size_t resolve_devices(size_t requested);
+// creates the device contexts a call with `requested` devices will use (CUDA start-up: driver initialisation,
+// context and module load), so a caller can overlap it with its own file work; errors surface at the first codec call
+void warm_up(size_t requested) noexcept;
 }  // namespace lacb_host

@@ -160,3 +160,35 @@ def test_decode_size_cap_and_opt_in(cli, tmp_path):
     assert not (tmp_path / "o.wav").exists()
     res = _run(cli, "decode", str(bad), str(tmp_path / "o.wav"), "--allow-large")
     assert res.returncode == 1 and "[decode-error] block=0 channel=primary" in res.stderr  # now it gets as far as the device
+
+
+def test_resident_server_forwards_commands(cli, tmp_path):
+    """`lac_cli serve` keeps the CUDA context alive; clients with LAC_SERVER set forward encode / decode to it and get
+    the same files, output text and exit status as a local run; without a listener they run locally."""
+    import time
+    sock = str(tmp_path / "s.sock")
+    srv = subprocess.Popen([cli, "serve", sock], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    try:
+        assert "serving on" in srv.stdout.readline()
+        env = dict(os.environ, LAC_SERVER=sock)
+        l, r, pk = H.synth(11, 4 * 16384 + 7, 24, want_packed=True)
+        wav, lac, back = tmp_path / "in.wav", tmp_path / "o.lac", tmp_path / "b.wav"
+        _write_wav(wav, pk, 2, 48000, 24)
+        t0 = time.perf_counter()
+        e = subprocess.run([cli, "encode", "in.wav", "o.lac"], capture_output=True, text=True, env=env, cwd=tmp_path)
+        d = subprocess.run([cli, "decode", str(lac), str(back)], capture_output=True, text=True, env=env)
+        dt = time.perf_counter() - t0
+        assert e.returncode == 0 and d.returncode == 0, e.stderr + d.stderr
+        assert e.stdout.startswith("Encoded ") and "samples per channel" in d.stdout
+        assert lac.read_bytes() == H.oracle().encode(l, r, 48000, 24, 2) and back.read_bytes() == wav.read_bytes()
+        assert dt < 2.0  # two forwarded commands: no CUDA start-up in either
+        bad = subprocess.run([cli, "decode", str(wav), str(tmp_path / "x.wav")], capture_output=True, text=True, env=env)
+        assert bad.returncode == 1 and "Decode failed" in bad.stderr
+        assert subprocess.run([cli, "shutdown"], env=env, capture_output=True).returncode == 0
+        assert srv.wait(timeout=30) == 0
+        # nobody listens any more: the same command line runs locally
+        e2 = subprocess.run([cli, "encode", str(wav), str(tmp_path / "o2.lac")], capture_output=True, text=True, env=env)
+        assert e2.returncode == 0 and (tmp_path / "o2.lac").read_bytes() == lac.read_bytes()
+    finally:
+        if srv.poll() is None:
+            srv.kill()
