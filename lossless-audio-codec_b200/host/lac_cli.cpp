@@ -319,9 +319,12 @@ static int run_batch(const char* argv0, const char* list_path) {
 static void milestone(const char* what) {
   static const bool on = std::getenv("LAC_TIMING") != nullptr;
   static const auto t0 = std::chrono::steady_clock::now();
-  if (on)
-    std::cerr << "[lac_cli " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()
-              << " ms] " << what << "\n";
+  if (on) {  // one write per line: the warm-up thread reports too
+    std::ostringstream line;
+    line << "[lac_cli " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()
+         << " ms] " << what << "\n";
+    std::cerr << line.str();
+  }
 }
 
 static int run_command(int argc, char** argv) {
@@ -376,7 +379,10 @@ static int run_command(int argc, char** argv) {
     if (threads == 0) threads = LAC::parse_thread_limit(std::getenv("LAC_THREADS"));
     // CUDA start-up (driver initialisation, context, module load: the largest fixed cost of a one-shot run)
     // proceeds on its own thread while this one maps the input file
-    std::thread warm([devices] { lacb_host::warm_up(devices); });
+    std::thread warm([devices] {
+      lacb_host::warm_up(devices);
+      milestone("cuda ready");
+    });
     struct Joiner {
       std::thread& t;
       ~Joiner() { if (t.joinable()) t.join(); }
@@ -392,8 +398,6 @@ static int run_command(int argc, char** argv) {
         return 1;
       }
       milestone("wav mapped");
-      warm.join();
-      milestone("cuda ready");
       LAC::ThreadCollector tc;
       LAC::Encoder enc(12, stereo_mode, info.sample_rate, info.bit_depth);
       enc.set_partitioning_enabled(partitioning);
@@ -434,8 +438,6 @@ static int run_command(int argc, char** argv) {
       return 1;
     }
     milestone("lac mapped");
-    warm.join();
-    milestone("cuda ready");
     LAC::ThreadCollector tc;
     LAC::Decoder dec(&tc);
     dec.set_thread_count(threads);

@@ -502,6 +502,14 @@ bool pin_files() {
   return on;
 }
 
+// helper threads for host-side page work: the caller's --threads cap, else the machine's cores, at most 16
+unsigned host_helpers(size_t thread_cap) {
+  unsigned n = std::thread::hardware_concurrency();
+  if (n == 0) n = 1;
+  if (thread_cap && thread_cap < n) n = (unsigned)thread_cap;
+  return std::min(n, 16u);
+}
+
 lacb_enc_params make_enc_params(uint32_t rate, uint8_t depth, uint8_t channels, uint8_t stereo_mode, bool zr, bool part) {
   lacb_enc_params prm{};
   prm.sample_rate = rate;
@@ -751,7 +759,11 @@ uint64_t Encoder::encode_packed_to_file(const uint8_t* pcm, uint64_t frames, uin
   const uint64_t cap = pcm_bytes + pcm_bytes / 8 + (uint64_t)nb * 64 + 4096;
   MappedFile mf;
   if (!mf.create(path, head + cap)) throw std::runtime_error("failed to create LAC output");
+  // the pages of the new file are faulted in on helper threads while CUDA starts up (ctx_for waits for a
+  // warm-up in flight); the payload rarely needs more than 3/4 of the PCM size, the rest faults on demand
+  mf.populate_async(head + pcm_bytes - pcm_bytes / 4, host_helpers(thread_count_));
   lacb_ctx* ctx0 = ctx_for(0);
+  mf.wait_populated();
   const bool pinned = pin_files() && lacb_host_register(ctx0, mf.data, mf.size) == 0;
   auto unpin = [&] {
     if (pinned) lacb_host_unregister(ctx0, mf.data);
@@ -836,7 +848,9 @@ void Decoder::decode_packed_to_file(const uint8_t* data, size_t size, const std:
   MappedFile mf;
   if (!mf.create(path, head.size() + pcm_bytes + (pcm_bytes & 1u))) throw std::runtime_error("failed to create WAV output");
   std::memcpy(mf.data, head.data(), head.size());
+  mf.populate_async(mf.size, host_helpers(thread_count_));  // under the CUDA start-up, see encode_packed_to_file
   lacb_ctx* ctx0 = ctx_for(0);
+  mf.wait_populated();
   const bool pinned = pin_files() && lacb_host_register(ctx0, mf.data, mf.size) == 0;
   try {
     run_decode(pf, LACB_PACKED_LE, mf.data + head.size(), nullptr, collector_, device_count_, thread_count_);

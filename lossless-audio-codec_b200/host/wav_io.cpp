@@ -5,6 +5,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 
@@ -53,12 +54,42 @@ bool MappedFile::create(const std::string& path, uint64_t bytes) {
 }
 bool MappedFile::resize(uint64_t bytes) {
   if (fd < 0 || !writable) return false;
+  wait_populated();
   if (data) ::munmap(data, size);
   data = nullptr;
   size = 0;
   return ::ftruncate(fd, (off_t)bytes) == 0;
 }
+void MappedFile::populate_async(uint64_t bytes, unsigned threads) {
+  wait_populated();
+  if (!data || !writable || size == 0) return;
+  bytes = std::min<uint64_t>(bytes, size);
+  threads = std::max(1u, std::min(threads, 32u));
+  constexpr uint64_t kAlign = 2ull << 20;
+  const uint64_t per = ((bytes + threads - 1) / threads + kAlign - 1) & ~(kAlign - 1);
+  for (uint64_t off = 0; off < bytes; off += per) {
+    uint8_t* p = data + off;
+    const uint64_t len = std::min<uint64_t>(per, bytes - off);
+    helpers_.emplace_back([p, len] {
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
+      if (::madvise(p, len, MADV_POPULATE_WRITE) == 0) return;
+      // older kernels: touch every page (a fresh file reads as zeros, so writing the byte back changes nothing)
+      for (uint64_t i = 0; i < len; i += 4096) {
+        volatile uint8_t* q = p + i;
+        *q = *q;
+      }
+    });
+  }
+}
+void MappedFile::wait_populated() {
+  for (std::thread& t : helpers_)
+    if (t.joinable()) t.join();
+  helpers_.clear();
+}
 void MappedFile::close() {
+  wait_populated();
   if (data) ::munmap(data, size);
   if (fd >= 0) ::close(fd);
   data = nullptr;

@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 struct WavInfo {
@@ -39,6 +40,14 @@ struct MappedFile {
   bool create(const std::string& path, uint64_t bytes);
   bool resize(uint64_t bytes);  // shrinks / grows the file; the mapping is dropped (call before close)
   void close();
+  // Faults the first `bytes` of a writable mapping in on `threads` helper threads (MADV_POPULATE_WRITE per
+  // range; a fresh file is otherwise faulted page by page by whoever copies into it, one thread, ~1.4 GB/s on
+  // the bench box).  Returns at once; wait_populated() joins the helpers (close() and the destructor do too).
+  void populate_async(uint64_t bytes, unsigned threads);
+  void wait_populated();
+
+ private:
+  std::vector<std::thread> helpers_;
 };
 // Parses the RIFF / RF64 structure of a WAV held in memory (same accept / reject rules as read_wav_packed) and
 // returns where the sample bytes are: nothing is copied.  RF64 (EBU Tech 3306: 'RF64' + 'ds64' chunk carrying the

@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# gpurun with retries while the pod answers "busy / transient" (exit 3, nothing charged).
+# usage: tools/gpurun_retry.sh <timeout-seconds> '<command>'
+T=$1; shift
+for attempt in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  echo "[retry] attempt $attempt answered busy; sleeping 90 s" >&2
+  sleep 90
+done
+exit 3
