@@ -23,7 +23,7 @@ def funcs(fn):
             m=re.search(r'(\w+)\s*\(', l.split('__forceinline__')[-1])
             if m: out.append((i,m.group(1)))
     return out
-for fn in ('lacb_encode.cuh','lacb_encode_fast.cuh','lacb_common.cuh','lacb_enc_kernels.cuh'):
+for fn in ('lacb_encode.cuh','lacb_common.cuh','lacb_enc_kernels.cuh','lacb_dec_kernels.cuh'):
     fs=funcs(fn)
     agg=collections.OrderedDict()
     for (f_,l),(i,s,_) in lines.items():
