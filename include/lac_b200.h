@@ -179,6 +179,27 @@ typedef struct lacb_block_info {
 } lacb_block_info;
 int lacb_last_block_info(lacb_ctx* ctx, lacb_block_info* info);
 
+/* Debug: the decisions of every block of the last lacb_encode / lacb_encode_to / lacb_encode_device call on this
+ * context -- what the reference's Debug build logs with --debug-lpc, --debug-zr, --debug-partitions and
+ * --debug-stereo-est (src/codec/block/encoder.cpp:457-466, 527-551, 824-835; src/codec/lac/encoder.cpp:356-379).
+ * The records live in the context's workspace, so the call must have run as one pass: lacb_set_concurrency(ctx, 1)
+ * before a host-buffer encode (the sliced pipeline reuses its workspaces and keeps the last slice only; the call
+ * then fails with LACB_EINVAL).  ch[0] / ch[1] are the channel-blocks as emitted (left / right or mid / side). */
+enum { LACB_DEC_MS = 1, LACB_DEC_UNCERTAIN = 2, LACB_DEC_PROBED = 4, LACB_DEC_BOTH = 8 };
+typedef struct lacb_chan_decision {
+  uint8_t predictor_type, order, partition_order, taps;
+  uint8_t base_mode, has_run, pad[2];
+  uint32_t bits, bytes;                                        /* exact emitted size */
+  uint64_t est_bits, rice_bits, zr_bits, bin_bits, static_bits; /* the winning predictor's estimates */
+  uint32_t level_bits[9];                                       /* total of partition level p; [0] = unpartitioned; 0 = not evaluated */
+} lacb_chan_decision;
+typedef struct lacb_block_decision {
+  uint32_t flags;      /* LACB_DEC_* */
+  uint32_t block_size; /* frames */
+  lacb_chan_decision ch[2];
+} lacb_block_decision;
+int lacb_last_encode_decisions(lacb_ctx* ctx, lacb_block_decision* out, uint32_t capacity, uint32_t* n_blocks);
+
 #ifdef __cplusplus
 }
 #endif

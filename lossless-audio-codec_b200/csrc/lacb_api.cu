@@ -45,6 +45,9 @@ struct lacb_ctx {
   cudaEvent_t ev_misc = nullptr;    // hmisc has landed
   std::vector<lacb_ctx*> kids;      // slice contexts of the pipelined host paths (own stream + workspace)
   lacb_block_info last_info{};
+  // what lacb_last_encode_decisions reads: the analysis that last ran in THIS context's workspace
+  uint32_t last_enc_blocks = 0, last_enc_channels = 0;
+  uint64_t last_enc_frames = 0;
   uint32_t max_streams = 0;         // lacb_set_concurrency: 0 = automatic, n = at most n slices in flight
 };
 
@@ -122,6 +125,9 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
   cfg.n_blocks = nb;
   PcmSrc src{dL, prm->channels == 2 ? dR : nullptr, frames};
   const bool automs = cfg.stereo_mode == 2u;
+  ctx->last_enc_blocks = nb;
+  ctx->last_enc_channels = prm->channels;
+  ctx->last_enc_frames = frames;
 
   CKR(ensure(ctx, ctx->flags, (size_t)nb * 4));
   CKR(ensure(ctx, ctx->jobs, (size_t)nb * 4 * 4));
@@ -686,6 +692,7 @@ static int encode_host(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, co
   }
   if (payload_out) *payload_out = nullptr;
   *payload_bytes = 0;
+  ctx->last_enc_blocks = 0;  // the sliced pipeline analyses in the slice contexts: nothing to report from here
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
@@ -788,6 +795,44 @@ int lacb_encode_block(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int zero_ru
     bi.part_k[i] = rec.part[i] & 31u;
   }
   for (int i = 0; i < 11; ++i) bi.cand_best_lo[i] = rec.cand_lo[i];
+  return 0;
+}
+
+int lacb_last_encode_decisions(lacb_ctx* ctx, lacb_block_decision* out, uint32_t capacity, uint32_t* n_blocks) {
+  if (!ctx || !n_blocks) return LACB_EINVAL;
+  const uint32_t nb = ctx->last_enc_blocks;
+  if (nb == 0u) {
+    ctx->err = "no single-pass encode to report (lacb_set_concurrency(ctx, 1) before the call)";
+    return LACB_EINVAL;
+  }
+  *n_blocks = nb;
+  if (!out) return 0;
+  if (capacity < nb) return LACB_ENOMEM;
+  CK(cudaSetDevice(ctx->device));
+  std::vector<ChanRec> recs((size_t)nb * 4);
+  std::vector<uint32_t> flags(nb);
+  CK(cudaMemcpy(recs.data(), ctx->recs.p, recs.size() * sizeof(ChanRec), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(flags.data(), ctx->flags.p, (size_t)nb * 4, cudaMemcpyDeviceToHost));
+  for (uint32_t b = 0; b < nb; ++b) {
+    lacb_block_decision& d = out[b];
+    memset(&d, 0, sizeof d);
+    const uint32_t f = flags[b];
+    const bool ms = ctx->last_enc_channels == 2u && (f & BF_CHOOSE_MS);
+    d.flags = (ms ? LACB_DEC_MS : 0u) | ((f & BF_UNCERTAIN) ? LACB_DEC_UNCERTAIN : 0u) |
+              ((f & BF_PROBE) ? LACB_DEC_PROBED : 0u) | ((f & BF_BOTH) ? LACB_DEC_BOTH : 0u);
+    const uint64_t left = ctx->last_enc_frames - (uint64_t)b * kMaxBlock;
+    d.block_size = left < kMaxBlock ? (uint32_t)left : kMaxBlock;
+    for (uint32_t c = 0; c < ctx->last_enc_channels; ++c) {
+      const ChanRec& r = recs[(size_t)b * 4 + (ms ? 2u : 0u) + c];
+      lacb_chan_decision& o = d.ch[c];
+      o.predictor_type = r.type; o.order = r.order; o.partition_order = r.p; o.taps = r.taps;
+      o.base_mode = r.base_mode; o.has_run = r.has_run;
+      o.bits = r.bits; o.bytes = r.bytes;
+      o.est_bits = r.est_best; o.rice_bits = r.est_rice; o.zr_bits = r.est_zr; o.bin_bits = r.est_bin;
+      o.static_bits = r.est_stat;
+      for (int p = 0; p < 9; ++p) o.level_bits[p] = r.lvl_bits[p];
+    }
+  }
   return 0;
 }
 

@@ -601,6 +601,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     best_total += (8ull - (best_total & 7ull)) & 7ull;
     uint32_t best_p = 0u;
     if (tid == 0u) sm.SelMK()[0] = (uint8_t)((base_mode << 5) | base_k);
+    if (!PROBE && tid < 9u) recs[slot].lvl_bits[tid] = tid ? 0u : (uint32_t)best_total;
     __syncthreads();
 
     // partition search, block/encoder.cpp:486-545
@@ -638,6 +639,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       __syncthreads();
       for (uint32_t p = 1u; p <= max_p; ++p) {
         const u64 total = mi->lvl_total[p];
+        if (!PROBE && tid == 0u) recs[slot].lvl_bits[p] = (uint32_t)total;
         const u64 margin = best_total / 20ull;
         if (total < best_total || (total <= best_total + margin && best_p == 0u) ||
             (total == best_total && p < best_p)) {  // :538-540
@@ -675,6 +677,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       const u64 sum_bits = warp_sum_u64(part_sum);
       u64 total = sum_bits + 8ull + 7ull * cnt;
       total += (8ull - (total & 7ull)) & 7ull;
+      if (!PROBE && tid == 0u) recs[slot].lvl_bits[p] = (uint32_t)total;
       const u64 margin = best_total / 20ull;
       if (total < best_total || (total <= best_total + margin && best_p == 0u) ||
           (total == best_total && p < best_p)) {  // :538-540
@@ -733,6 +736,11 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         rec->taps = (uint8_t)best.taps;
         for (int i = 0; i < 13; ++i) rec->coef[i] = (wcoef && i >= 1 && (uint32_t)i <= chosen_order) ? wcoef[i] : (int16_t)0;
         rec->pad = 0;
+        rec->base_mode = (uint8_t)base_mode;
+        rec->has_run = (uint8_t)(best.has_run != 0u);
+        rec->pad2[0] = rec->pad2[1] = 0;
+        rec->est_best = best.best; rec->est_rice = best.rice; rec->est_zr = best.zr; rec->est_bin = best.bin;
+        rec->est_stat = best.stat;
       }
     }
     __syncthreads();

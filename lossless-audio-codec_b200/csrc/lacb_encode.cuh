@@ -40,6 +40,10 @@ struct ChanRec {
   uint8_t part[256];   // (mode << 5) | k per partition
   uint16_t pad;
   uint32_t cand_lo[11];  // debug: low 32 bits of every candidate's best_bits (0xFFFFFFFF = skipped)
+  // decision dump (lacb_last_encode_decisions): the winner's estimates and the total of every partition level
+  uint32_t lvl_bits[9];  // byte-rounded total of level p (block/encoder.cpp:527-529); [0] = unpartitioned; 0 = not evaluated
+  uint8_t base_mode, has_run, pad2[2];
+  u64 est_best, est_rice, est_zr, est_bin, est_stat;  // block/encoder.cpp:824-835, 457-466
 };
 
 __device__ __forceinline__ int32_t load_sample(const PcmSrc& s, int kind, u64 idx) {

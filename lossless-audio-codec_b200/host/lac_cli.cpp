@@ -29,7 +29,7 @@ namespace {
 void usage() {
   std::cerr << "Usage:\n"
             << "  lac_cli encode input.wav output.lac [--stereo-mode=lr|ms] [--threads=N] [--devices=N] "
-               "[--debug-threads] [--no-partitioning] [--allow-large]\n"
+               "[--debug-threads] [--debug-lpc] [--debug-stereo-est] [--debug-zr] [--debug-partitions] [--no-partitioning] [--allow-large]\n"
             << "  lac_cli decode input.lac output.wav [--threads=N] [--devices=N] [--debug-threads] [--allow-large]\n"
             << "  lac_cli selftest\n"
             << "  lac_cli batch list.txt        (one encode/decode command per line, one process)\n"
@@ -359,6 +359,7 @@ static int run_command(int argc, char** argv) {
     uint8_t stereo_mode = 2;
     size_t threads = 0, devices = 0;
     bool debug_threads = false, partitioning = true, allow_large = false;
+    bool debug_lpc = false, debug_stereo_est = false, debug_zr = false, debug_partitions = false;
     for (int i = 4; i < argc; ++i) {
       const std::string a = argv[i];
       if (a == "--stereo-mode=lr") stereo_mode = 0;
@@ -369,8 +370,11 @@ static int run_command(int argc, char** argv) {
       else if (a == "--debug-threads") debug_threads = true;
       else if (a == "--no-partitioning") partitioning = false;
       else if (a == "--allow-large") allow_large = true;
-      else if (a == "--debug-lpc" || a == "--debug-stereo-est" || a == "--debug-zr" || a == "--debug-partitions") {
-      } else {
+      else if (a == "--debug-lpc") debug_lpc = true;
+      else if (a == "--debug-stereo-est") debug_stereo_est = true;
+      else if (a == "--debug-zr") debug_zr = true;
+      else if (a == "--debug-partitions") debug_partitions = true;
+      else {
         std::cerr << "Unknown option: " << a << "\n";
         usage();
         return 1;
@@ -399,7 +403,8 @@ static int run_command(int argc, char** argv) {
       }
       milestone("wav mapped");
       LAC::ThreadCollector tc;
-      LAC::Encoder enc(12, stereo_mode, info.sample_rate, info.bit_depth);
+      LAC::Encoder enc(12, stereo_mode, info.sample_rate, info.bit_depth, debug_lpc, debug_stereo_est, debug_zr);
+      enc.set_debug_partitions(debug_partitions);
       enc.set_partitioning_enabled(partitioning);
       enc.set_thread_count(threads);
       enc.set_device_count(devices);
@@ -420,6 +425,16 @@ static int run_command(int argc, char** argv) {
         throw;
       }
       milestone("encoded");
+      if (debug_zr) {  // src/main.cpp:676-690: the same file without zero-run tokens, for comparison
+        LAC::Encoder baseline(12, stereo_mode, info.sample_rate, info.bit_depth, debug_lpc, debug_stereo_est, false);
+        baseline.set_zero_run_enabled(false);
+        baseline.set_partitioning_enabled(partitioning);
+        baseline.set_debug_partitions(debug_partitions);
+        baseline.set_thread_count(threads);
+        const std::vector<uint8_t> base = baseline.encode_packed(in.data + data_off, info.frames, (uint8_t)info.channels);
+        const double gain = base.empty() ? 0.0 : (1.0 - (double)lac_bytes / (double)base.size()) * 100.0;
+        std::cout << "[debug-zr] baseline_bytes=" << base.size() << " zr_bytes=" << lac_bytes << " gain=" << gain << "%\n";
+      }
       if (!st.publish()) {
         std::cerr << "Failed to write LAC file: " << out_path << "\n";
         return 1;

@@ -6,7 +6,9 @@
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
+#include <iostream>
 #include <limits>
+#include <sstream>
 #include <stdexcept>
 
 #include "../../include/lac_b200.h"
@@ -665,8 +667,56 @@ size_t parse_thread_limit(const char* value) {
   return (size_t)v;
 }
 
-Encoder::Encoder(uint8_t order, uint8_t stereo_mode, uint32_t sample_rate, uint8_t bit_depth, bool, bool, bool)
-    : order_(order), stereo_mode_(stereo_mode), sample_rate_(sample_rate), bit_depth_(bit_depth) {}
+Encoder::Encoder(uint8_t order, uint8_t stereo_mode, uint32_t sample_rate, uint8_t bit_depth, bool debug_lpc,
+                 bool debug_stereo_est, bool debug_zr)
+    : order_(order), stereo_mode_(stereo_mode), sample_rate_(sample_rate), bit_depth_(bit_depth),
+      debug_lpc_(debug_lpc), debug_stereo_est_(debug_stereo_est), debug_zr_(debug_zr) {}
+
+// The decision log of a whole file in the words of the reference's Debug build (LAC_DEBUG_LOG is compiled out of
+// its Release build): [stereo-est] / [stereo-mode] (src/codec/lac/encoder.cpp:356-379), [zr-est], [part-est],
+// [part-choose] and [debug-lpc] (src/codec/block/encoder.cpp:457-466, 527-551, 824-835), one block after the other
+// and only for the channel-blocks that were emitted (the reference also logs its probe and both-pair encodes, in
+// worker order).  `energy` (the Levinson error of an LPC winner) is not kept on the device and is left out.
+void Encoder::print_decisions(lacb_ctx* ctx, uint8_t mode) const {
+  uint32_t nb = 0;
+  if (lacb_last_encode_decisions(ctx, nullptr, 0, &nb) != 0)
+    throw std::runtime_error(std::string("LAC B200 backend: ") + lacb_last_error(ctx));
+  std::vector<lacb_block_decision> dec(nb);
+  if (lacb_last_encode_decisions(ctx, dec.data(), nb, &nb) != 0)
+    throw std::runtime_error(std::string("LAC B200 backend: ") + lacb_last_error(ctx));
+  std::ostringstream out;
+  for (uint32_t b = 0; b < nb; ++b) {
+    const lacb_block_decision& d = dec[b];
+    const bool stereo = d.ch[1].bytes != 0;
+    const bool ms = (d.flags & LACB_DEC_MS) != 0;
+    for (int c = 0; c < (stereo ? 2 : 1); ++c) {
+      const lacb_chan_decision& ch = d.ch[c];
+      if (debug_zr_ && zero_run_enabled_)
+        out << "[zr-est] block=" << b << " normal=" << ch.rice_bits << " zr=" << ch.zr_bits << " bin=" << ch.bin_bits
+            << " static=" << ch.static_bits << " chosen=" << (int)ch.base_mode << " has_run=" << (int)ch.has_run << "\n";
+      if (debug_partitions_ && partitioning_enabled_ && d.block_size >= 64) {
+        for (uint32_t p = 1; p < 9; ++p)
+          if (ch.level_bits[p])
+            out << "[part-est] block=" << b << " p=" << p << " bits=" << ch.level_bits[p] << " partitions=" << (1u << p)
+                << "\n";
+        out << "[part-choose] block=" << b << " best_p=" << (uint32_t)ch.partition_order
+            << " bits=" << ch.level_bits[ch.partition_order] << "\n";
+      }
+      if (debug_lpc_)
+        out << "[debug-lpc] block=" << d.block_size << " chosen_order=" << (int)ch.order
+            << " predictor=" << (int)ch.predictor_type << " est_bits=" << ch.est_bits << " rice_bits=" << ch.rice_bits
+            << " zr_bits=" << ch.zr_bits << " bin_bits=" << ch.bin_bits << " part_order=" << (uint32_t)ch.partition_order
+            << "\n";
+    }
+    if (debug_stereo_est_ && stereo) {
+      if (mode == 2)
+        out << "[stereo-est] block=" << b << " uncertain=" << ((d.flags & LACB_DEC_UNCERTAIN) ? 1 : 0)
+            << " chosen=" << (ms ? "MS" : "LR") << "\n";
+      out << "[stereo-mode] global=" << (int)mode << " block=" << b << " mode_used=" << (ms ? "MS" : "LR") << "\n";
+    }
+  }
+  std::cerr << out.str();
+}
 
 void Encoder::check_config() const {
   if (!rate_ok(sample_rate_)) throw std::invalid_argument("unsupported sample rate: " + std::to_string(sample_rate_));
@@ -697,7 +747,11 @@ std::vector<uint8_t> Encoder::run(int layout, const void* a, const void* b, uint
                                   ThreadCollector* collector) {
   (void)order_;
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
-  const WorkerPlan plan = plan_workers(device_count_, thread_count_, nb);
+  WorkerPlan plan = plan_workers(device_count_, thread_count_, nb);
+  if (debug_any()) {  // the decision log is read from one context's workspace: one device, one pass
+    plan.devices = 1;
+    plan.streams = 1;
+  }
   const std::vector<Shard> shards = plan_shards(frames, plan.devices);
   const lacb_enc_params prm = make_enc_params(sample_rate_, bit_depth_, channels, stereo_mode_, zero_run_enabled_,
                                               partitioning_enabled_);
@@ -720,6 +774,7 @@ std::vector<uint8_t> Encoder::run(int layout, const void* a, const void* b, uint
     lacb_err err{};
     const int rc = lacb_encode(ctx, &prm, layout, a, b, frames, &slab, &slab_bytes, block_bytes.data(), &err);
     if (rc != 0) throw_encode_failure(rc, lacb_last_error(ctx), layout, a, b, frames, bit_depth_);
+    if (debug_any()) print_decisions(ctx, (uint8_t)prm.stereo_mode);
     out.resize(head);
     out.reserve(head + slab_bytes);
     out.insert(out.end(), slab, slab + slab_bytes);
@@ -743,7 +798,11 @@ uint64_t Encoder::encode_packed_to_file(const uint8_t* pcm, uint64_t frames, uin
   if (channels != 1 && channels != 2) throw std::invalid_argument("unsupported channel count");
   check_config();
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
-  const WorkerPlan plan = plan_workers(device_count_, thread_count_, nb);
+  WorkerPlan plan = plan_workers(device_count_, thread_count_, nb);
+  if (debug_any()) {
+    plan.devices = 1;
+    plan.streams = 1;
+  }
   const std::vector<Shard> shards = plan_shards(frames, plan.devices);
   const lacb_enc_params prm = make_enc_params(sample_rate_, bit_depth_, channels, stereo_mode_, zero_run_enabled_,
                                               partitioning_enabled_);
@@ -788,6 +847,7 @@ uint64_t Encoder::encode_packed_to_file(const uint8_t* pcm, uint64_t frames, uin
         return v.size();
       }
       if (rc != 0) throw_encode_failure(rc, lacb_last_error(ctx0), LACB_PACKED_LE, pcm, nullptr, frames, bit_depth_);
+      if (debug_any()) print_decisions(ctx0, (uint8_t)prm.stereo_mode);
     } else {
       total = encode_sharded(prm, LACB_PACKED_LE, pcm, nullptr, frames, shards, plan.streams, collector, block_bytes,
                              [&](uint64_t t) -> uint8_t* {

@@ -95,6 +95,8 @@ class BitWriter {
   int nbits_ = 0;                // bits held in cur_
 };
 
+struct lacb_ctx;
+
 namespace LAC {
 
 class ThreadCollector {
@@ -151,8 +153,12 @@ class Encoder {
   bool zero_run_enabled_ = true;
   bool partitioning_enabled_ = true;
   bool debug_partitions_ = false;
+  bool debug_lpc_ = false, debug_stereo_est_ = false, debug_zr_ = false;
   size_t thread_count_ = 0;
   size_t device_count_ = 0;
+  bool debug_any() const { return debug_partitions_ || debug_lpc_ || debug_stereo_est_ || debug_zr_; }
+  // prints the decision log of the encode that just ran on `ctx` (std::cerr, the reference's Debug-build lines)
+  void print_decisions(lacb_ctx* ctx, uint8_t effective_stereo_mode) const;
 };
 
 class Decoder {

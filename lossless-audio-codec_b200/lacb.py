@@ -56,7 +56,7 @@ class BlockInfo(C.Structure):
 
 EXPORTS = ("lacb_create", "lacb_destroy", "lacb_last_error", "lacb_free", "lacb_device_count", "lacb_get_timing",
            "lacb_encode", "lacb_encode_to", "lacb_encode_device", "lacb_decode", "lacb_decode_device", "lacb_encode_block",
-           "lacb_decode_block", "lacb_lpc_analyze", "lacb_last_block_info", "lacb_dev_malloc", "lacb_dev_free",
+           "lacb_decode_block", "lacb_lpc_analyze", "lacb_last_block_info", "lacb_last_encode_decisions", "lacb_dev_malloc", "lacb_dev_free",
            "lacb_host_malloc", "lacb_host_free", "lacb_memcpy_h2d", "lacb_memcpy_d2h", "lacb_memcpy_d2d",
            "lacb_decode_block_at", "lacb_set_concurrency", "lacb_host_register", "lacb_host_unregister")
 
