@@ -584,6 +584,206 @@ __device__ __forceinline__ bool decode_segment_fast(BitRd& r, u64& pos, uint32_t
   return true;
 }
 
+// Warp-cooperative decode of an UNPARTITIONED adaptive segment (stateful model: Rice::adapt_k with the drift and
+// micro windows, rice.hpp:45-114) in Rice or bin mode, by the same speculation as decode_segment_fast: lane 0 places
+// the boundaries of a batch assuming "k stays k", lane t extracts token t, and the k that follows every token is
+// recomputed exactly from prefix sums --
+//   base k     from sum + prefix of u and the sample count (closed form, kbase_clz),
+//   drift rule from the 256-sample window sum: the running window sum plus the prefix of (u entering - u leaving),
+//              the leaving value read from the 256-entry ring of committed samples,
+//   micro rule from the counts of "large" / "zero" quotient flags over the last 96 samples: the running counts plus
+//              popcounts of the batch's flag ballots minus those of the flags leaving (the top word of the 96-bit
+//              flag history, bit-reversed so that bit t is the flag token t pushes out).
+// The first lane whose k differs from the assumed one ends the valid prefix; the committed tokens update the ring,
+// the flag history and the running sums, and the batch restarts behind them.  Tokens the walker cannot place go to
+// the exact serial reader (parse_token) and are folded into the state one sample at a time.
+// Zero-run mode is not handled here (a run token advances the model by many samples): the caller keeps the serial
+// reader for it.
+struct StatefulState {
+  u64 sum, win_sum;
+  uint32_t count;
+  uint32_t lg[3], zr[3];  // flag history, bit 0 = newest (as KState)
+  uint32_t Lc, Zc;        // set bits in lg / zr
+};
+__device__ __forceinline__ int stateful_bias(u64 N, uint32_t c, u64 win_sum, uint32_t Lc, uint32_t Zc) {
+  int bias = 0;
+  if (c >= kDriftWin && N >= (u64)c) {
+    const u64 lm = (win_sum + 128ull) >> 8;
+    const u64 tA = (3ull * lm + 3ull) >> 2;
+    if (N < tA * c) bias = 1;
+    else {
+      const u64 tB = lm + 2ull + lm / 3ull;
+      if (N >= tB * c) bias = -1;
+    }
+  }
+  if (c >= kMicroWin) {
+    if (Lc * 4u >= 288u) bias = bias + 1 < 1 ? bias + 1 : 1;
+    else if (Zc * 5u >= 384u) bias = bias - 1 > -1 ? bias - 1 : -1;
+  }
+  return bias;
+}
+// one sample folded into the state by every lane alike (lane 0 writes the ring); returns the next k
+__device__ __forceinline__ uint32_t stateful_step(StatefulState& st, uint32_t u, uint32_t* ring, uint32_t lane) {
+  st.sum += u;
+  const uint32_t c = ++st.count;
+  const u64 N = st.sum + (c >> 1);
+  const uint32_t kb = kbase_clz(N, c);
+  const uint32_t slot = (c - 1u) & (kDriftWin - 1u);
+  st.win_sum += u;
+  if (c > kDriftWin) st.win_sum -= ring[slot];
+  __syncwarp();
+  if (lane == 0u) ring[slot] = u;
+  __syncwarp();
+  const uint32_t q = (kb >= 31u) ? 0u : (u >> kb);
+  const uint32_t is_l = q > 3u, is_z = q == 0u;
+  st.Lc += is_l - (st.lg[2] >> 31);
+  st.Zc += is_z - (st.zr[2] >> 31);
+  st.lg[2] = (st.lg[2] << 1) | (st.lg[1] >> 31);
+  st.lg[1] = (st.lg[1] << 1) | (st.lg[0] >> 31);
+  st.lg[0] = (st.lg[0] << 1) | is_l;
+  st.zr[2] = (st.zr[2] << 1) | (st.zr[1] >> 31);
+  st.zr[1] = (st.zr[1] << 1) | (st.zr[0] >> 31);
+  st.zr[0] = (st.zr[0] << 1) | is_z;
+  const int k = (int)kb + stateful_bias(N, c, st.win_sum, st.Lc, st.Zc);
+  return (uint32_t)(k < 0 ? 0 : (k > 31 ? 31 : k));
+}
+// Not inlined (and everything passed by value) so that the register allocation of the partitioned path, the one
+// every benchmark stream takes, is not touched by this one.  Returns the bit position behind the segment, or
+// ~0 when the segment is rejected.
+#ifdef LACB_EMU
+#define LACB_NOINLINE
+#else
+#define LACB_NOINLINE __noinline__
+#endif
+__device__ LACB_NOINLINE u64 decode_segment_stateful(BitRd r, u64 pos, uint32_t n, uint32_t k0, uint32_t mode,
+                                                     int32_t* res, uint32_t* ring, ParseScratch* sc, uint32_t lane) {
+  constexpr u64 kReject = ~0ull;
+  if (k0 > 31u) return kReject;
+  Stage stg = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFEu, 0u, 0u};
+  StatefulState st;
+  st.sum = st.win_sum = 0ull;
+  st.count = 0u;
+  st.lg[0] = st.lg[1] = st.lg[2] = st.zr[0] = st.zr[1] = st.zr[2] = 0u;
+  st.Lc = st.Zc = 0u;
+  uint32_t idx = 0u, k = k0, B = 8u;
+  const uint32_t le = 0xFFFFFFFFu >> (31u - lane);  // lanes 0..lane
+  while (idx < n) {
+    const uint32_t left = n - idx;
+    const uint32_t want = k > 26u ? 0u : (B < left ? B : left);
+    stage_ensure(r, sc, stg, pos, lane);
+    const uint32_t rel0 = (uint32_t)pos & 4095u;
+    const u64 ring_base = pos - rel0;
+    uint32_t cnt = 0u;
+    if (lane == 0u && want) cnt = walk_tokens(sc->ring, sc->tp, rel0, mode, k, want);
+    cnt = __shfl_sync(kFull, cnt, 0);
+    __syncwarp();
+    uint32_t u = 0u;
+    bool bad = false;
+    if (lane < cnt) {
+      const uint32_t s = sc->tp[lane], e = sc->tp[lane + 1u];
+      bad = ring_base + e > r.end;
+      if (mode == MODE_RICE) {
+        const uint32_t rem = k ? ring_peek(sc->ring, e - k) >> (32u - k) : 0u;
+        const uint32_t q = e - s - 1u - k;
+        bad = bad || q >= 32u;
+        u = (q << k) | rem;
+      } else {  // MODE_BIN
+        const uint32_t hs = ring_peek(sc->ring, s);
+        const uint32_t tag = hs >> 30;
+        if (tag != 3u) {
+          const uint32_t sign = (hs >> 29) & 1u;
+          u = tag == 0u ? 0u : (tag == 1u ? (sign ? 1u : 2u) : (sign ? 3u : 4u));
+        } else {
+          const uint32_t rem = k ? ring_peek(sc->ring, e - k) >> (32u - k) : 0u;
+          u = ((e - s - 3u - k) << k) | rem;
+        }
+      }
+    }
+    const bool live = lane < cnt && !bad;
+    // prefix of u and of (u - the sample leaving the drift window)
+    const uint32_t c = st.count + lane + 1u;
+    const uint32_t slot = (c - 1u) & (kDriftWin - 1u);
+    const uint32_t leave = (live && c > kDriftWin) ? ring[slot] : 0u;
+    u64 PU = live ? u : 0u;
+    i64 PD = live ? (i64)u - (i64)leave : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 yu = __shfl_up_sync(kFull, PU, d);
+      const i64 yd = __shfl_up_sync(kFull, PD, d);
+      if (lane >= (uint32_t)d) {
+        PU += yu;
+        PD += yd;
+      }
+    }
+    const u64 N = st.sum + PU + (c >> 1);
+    const uint32_t kb = kbase_clz(N, c);
+    const uint32_t q = (kb >= 31u) ? 0u : (u >> kb);
+    const uint32_t BL = __ballot_sync(kFull, live && q > 3u), BZ = __ballot_sync(kFull, live && q == 0u);
+    const uint32_t outL = __brev(st.lg[2]), outZ = __brev(st.zr[2]);  // bit t: the flag token t pushes out
+    const uint32_t Lc = st.Lc + (uint32_t)__popc(BL & le) - (uint32_t)__popc(outL & le);
+    const uint32_t Zc = st.Zc + (uint32_t)__popc(BZ & le) - (uint32_t)__popc(outZ & le);
+    const u64 ws = (u64)((i64)st.win_sum + PD);
+    const int kk = (int)kb + stateful_bias(N, c, ws, Lc, Zc);
+    const uint32_t knext = (uint32_t)(kk < 0 ? 0 : (kk > 31 ? 31 : kk));
+    const uint32_t mbad = __ballot_sync(kFull, bad);
+    const uint32_t mism = __ballot_sync(kFull, lane < cnt && knext != k);
+    uint32_t valid = mism ? (uint32_t)__ffs((int)mism) : cnt;
+    const uint32_t first_bad = mbad ? (uint32_t)__ffs((int)mbad) - 1u : cnt;
+    if (valid > first_bad) valid = first_bad;
+    uint32_t knew = k;
+    if (valid) {
+      if (lane < valid) {
+        res[idx + lane] = unzz32(u);
+        ring[slot] = u;
+      }
+      const int last = (int)valid - 1;
+      knew = __shfl_sync(kFull, knext, last);
+      st.sum += __shfl_sync(kFull, PU, last);
+      st.win_sum = __shfl_sync(kFull, ws, last);
+      st.Lc = __shfl_sync(kFull, Lc, last);
+      st.Zc = __shfl_sync(kFull, Zc, last);
+      st.count += valid;
+      idx += valid;
+      pos = ring_base + sc->tp[valid];
+      // flag history: `valid` new flags, newest (token valid - 1) at bit 0
+      const uint32_t insL = __brev(BL << (32u - valid)), insZ = __brev(BZ << (32u - valid));
+      st.lg[2] = __funnelshift_lc(st.lg[1], st.lg[2], valid);
+      st.lg[1] = __funnelshift_lc(st.lg[0], st.lg[1], valid);
+      st.lg[0] = __funnelshift_lc(0u, st.lg[0], valid) | insL;
+      st.zr[2] = __funnelshift_lc(st.zr[1], st.zr[2], valid);
+      st.zr[1] = __funnelshift_lc(st.zr[0], st.zr[1], valid);
+      st.zr[0] = __funnelshift_lc(0u, st.zr[0], valid) | insZ;
+    }
+    __syncwarp();
+    if (knew != k) {
+      k = knew;
+      B = valid < 4u ? 4u : valid;
+      continue;
+    }
+    if (valid == cnt && cnt == want && want) {
+      B = B * 2u > 32u ? 32u : B * 2u;
+      continue;
+    }
+    if (idx >= n) break;
+    // a token the walker could not place (or one that runs past the data): the exact reader, one sample
+    uint32_t ok = 0u, su = 0u, sw = 0u;
+    u64 npos = 0ull;
+    if (lane == 0u) {
+      rd_seek(r, pos);
+      ok = parse_token(r, mode, k, &su, &sw) && !rd_over(r);
+      npos = rd_pos(r);
+    }
+    ok = __shfl_sync(kFull, ok, 0);
+    if (!ok) return kReject;
+    su = __shfl_sync(kFull, su, 0);
+    pos = __shfl_sync(kFull, npos, 0);
+    if (lane == 0u) res[idx] = unzz32(su);
+    idx += 1u;
+    k = stateful_step(st, su, ring, lane);
+  }
+  return pos;
+}
+
 // Header + residual part of Block::Decoder::decode_into (block/decoder.cpp:64-512): leaves
 // the residual in `out` and the predictor description in `hdr`.  Warp collective: every
 // lane calls it, lane 0 owns the reader.
@@ -651,7 +851,13 @@ __device__ __forceinline__ bool parse_channel_block(BitRd& r, uint32_t n, int32_
     const uint32_t mode = mk >> 5, k0 = mk & 31u;
     if (p || mode == MODE_STATIC) {
       ok = decode_segment_fast(r, pos, len, k0, mode, out + off, sc, stg, lane) ? 1u : 0u;
-    } else {  // stateful adaptation (p == 0): the serial reader with the full model
+#ifndef LACB_STATEFUL_SERIAL  // (measurement builds only: the serial reader for every stateful segment)
+    } else if (mode != MODE_ZR) {  // stateful adaptation (p == 0), one sample per token: speculative batches
+      const u64 np = decode_segment_stateful(r, pos, len, k0, mode, out + off, ring, sc, lane);
+      ok = np != ~0ull;
+      if (ok) pos = np;
+#endif
+    } else {  // stateful zero-run mode: the serial reader with the full model
       if (lane == 0u) {
         rd_seek(r, pos);
         ok = decode_segment<false>(r, len, k0, mode, out + off, ring) ? 1u : 0u;

@@ -152,3 +152,13 @@ def test_partition_levels_share_segment_starts(cd):
     for b in (10, 44, 45):
         x = m[b * 16384:(b + 1) * 16384]
         assert cd.block_encode(x, True, True) == H.oracle().block_encode(x, True, True), b
+
+
+def test_unpartitioned_file_round_trip(cd):
+    """Unpartitioned streams: the stateful model by speculative batches (Rice / bin) and the serial reader (zero-run)."""
+    for seed, depth in ((2, 24), (1, 16)):
+        l, r = H.synth(seed, 3 * 16384 + 99, depth)
+        want = H.oracle().encode(l, r, 48000, depth, 1, partitioning=False)
+        assert cd.encode(l, r, 48000, depth, 1, partitioning=False) == want
+        dl, dr, _ = cd.decode(want)
+        assert np.array_equal(dl, l) and np.array_equal(dr, r)

@@ -158,7 +158,7 @@ def fuzz_block_decoder(cd, seed, names, flips):
     rejected = 0
     for name in names:
         pcm = corpus[name]
-        for zr, part in ((1, 1), (0, 1), (1, 0)):
+        for zr, part in ((1, 1), (0, 1), (1, 0), (0, 0)):
             good = H.oracle().block_encode(pcm, zr, part)
             trials = [good, good[:-1], good[: len(good) // 2], good + b"\0"]
             for _ in range(flips):
@@ -400,3 +400,14 @@ def test_concurrency_cap_same_bytes(cd):
             ref = cur
     finally:
         cd.set_concurrency(0)
+
+
+def test_unpartitioned_file_round_trip(cd):
+    """Streams written with partitioning disabled: every adaptive segment is decoded with the stateful model
+    (speculative batches for Rice / bin mode, the serial reader for zero-run mode)."""
+    for seed, depth in ((2, 24), (1, 16)):
+        l, r = H.synth(seed, 16 * 16384 + 99, depth)
+        want = H.oracle().encode(l, r, 48000, depth, 1, partitioning=False)
+        assert cd.encode(l, r, 48000, depth, 1, partitioning=False) == want
+        dl, dr, _ = cd.decode(want)
+        assert np.array_equal(dl, l) and np.array_equal(dr, r)
