@@ -1,6 +1,8 @@
 """k_analyze time per section type of the Appendix C signal (AR noise / triangle / sparse silence / stepped noise).
-usage: section_timing.py lib.so [lib2.so ...]"""
+usage: section_timing.py [--only=<section 0..3>] lib.so [lib2.so ...]   (--only: one section, e.g. under ncu)"""
 import sys
+only = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--only=")]
+sys.argv = [a for a in sys.argv if not a.startswith("--only=")]
 sys.path.insert(0, "tests")
 import numpy as np, helpers as H
 secs = 240
@@ -11,7 +13,7 @@ sec = (np.arange(nb) * 16384 >> 17) & 3
 names = ["AR(4) noise", "triangle", "sparse silence", "stepped noise"]
 for lib in sys.argv[1:]:
     cd = H.lacb_module().Codec(0, lib)
-    for s in range(4):
+    for s in (only or range(4)):
         ll = np.ascontiguousarray(l[sec == s]).reshape(-1); rr = np.ascontiguousarray(r[sec == s]).reshape(-1)
         pk = np.zeros(ll.size * 6, dtype=np.uint8)
         both = np.stack([ll, rr], axis=1).reshape(-1)
