@@ -411,16 +411,22 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       int32_t x[E + 12];
       load_items<NT, E>(sm, x);
       auto bound = [&](const int32_t (&r)[E]) -> uint32_t {
-        uint32_t a = 0u, z = 0u, n4 = 0u;
+        // |x| < 2^26 here, so every |residual| < 2^30, u < 2^31 and clz(u) >= 1: bit_width(u) + 1 = 33 - clz(u).
+        // Zeros (0 bits inside a run; missing samples past the block end are zeros too) and fours (3 bits as a
+        // bin code) need a correction, looked for only in chunks that hold a value <= 4.
+        uint32_t a = 0u, umin = 0xFFFFFFFFu;
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-          const uint32_t uu = zz32(r[j]);  // residuals past the block end are 0
-          const uint32_t lz = (uint32_t)__clz((int)uu);
-          a += lz ? lz : 1u;  // u >= 2^31: 32 bits, not 33
-          z += lz >> 5;       // zeros (and missing samples) cost nothing
-          n4 += uu == 4u ? 1u : 0u;
+          const uint32_t uu = zz32(r[j]);
+          a += (uint32_t)__clz((int)uu);
+          umin = uu < umin ? uu : umin;
         }
-        return 33u * (uint32_t)E - a - z - n4;
+        uint32_t lb = 33u * (uint32_t)E - a;
+        if (umin <= 4u) {
+#pragma unroll
+          for (int j = 0; j < E; ++j) lb -= ((zz32(r[j]) & ~4u) == 0u) ? 1u : 0u;  // u == 0 or u == 4
+        }
+        return lb;
       };
       auto publish = [&](uint32_t ci, uint32_t lbt) {
         const uint32_t t = warp_sum_u32(lbt);

@@ -220,12 +220,21 @@ __device__ __forceinline__ void load_items(const ASmem<NT, E>& sm, int32_t (&x)[
 
 // Fixed / FIR residuals, block/encoder.cpp:265-309.  The fixed predictors are exact
 // in wrapping 32-bit arithmetic (the reference truncates the int64 difference).
+// Samples past the block end and the predictor warm-up (the first `order` samples are verbatim) concern at most two
+// threads of a block: the main loops carry no per-sample tests, the two threads patch their chunk afterwards.
+template <int E>
+__device__ __forceinline__ void residual_tail(uint32_t g0, uint32_t n, int32_t (&r)[E]) {
+  if (g0 + (uint32_t)E > n) {
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+      if (g0 + j >= n) r[j] = 0;
+  }
+}
 template <int E>
 __device__ __forceinline__ void residual_fixed(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n, int order,
                                                int32_t (&r)[E]) {
 #pragma unroll
   for (int j = 0; j < E; ++j) {
-    const uint32_t idx = g0 + j;
     const uint32_t x0 = (uint32_t)x[12 + j], x1 = (uint32_t)x[11 + j], x2 = (uint32_t)x[10 + j],
                    x3 = (uint32_t)x[9 + j], x4 = (uint32_t)x[8 + j];
     uint32_t v;
@@ -236,20 +245,27 @@ __device__ __forceinline__ void residual_fixed(const int32_t (&x)[E + 12], uint3
       case 4: v = x0 - 4u * x1 + 6u * x2 - 4u * x3 + x4; break;
       default: v = x0; break;
     }
-    if (idx < (uint32_t)order) v = x0;
-    r[j] = idx < n ? (int32_t)v : 0;
+    r[j] = (int32_t)v;
   }
+  if (g0 == 0u) {
+#pragma unroll
+    for (int j = 0; j < 4 && j < E; ++j)
+      if (j < order) r[j] = x[12 + j];
+  }
+  residual_tail<E>(g0, n, r);
 }
 template <int E>
 __device__ __forceinline__ void residual_fir(const int32_t (&x)[E + 12], uint32_t g0, uint32_t n, int32_t (&r)[E]) {
 #pragma unroll
   for (int j = 0; j < E; ++j) {
-    const uint32_t idx = g0 + j;
     const i64 p = (3ll * (i64)x[11 + j] - (i64)x[10 + j]) >> 2;
-    uint32_t v = (uint32_t)(u64)((i64)x[12 + j] - p);
-    if (idx < 2u) v = (uint32_t)x[12 + j];
-    r[j] = idx < n ? (int32_t)v : 0;
+    r[j] = (int32_t)(uint32_t)(u64)((i64)x[12 + j] - p);
   }
+  if (g0 == 0u) {
+    r[0] = x[12];
+    if (E > 1) r[1] = x[13];
+  }
+  residual_tail<E>(g0, n, r);
 }
 // LPC residual with `TAPS` Q15 taps, lpc.cpp:38-61; returns true if any residual leaves int32
 // CHECK = false: the caller knows every |x| < 2^26, so |x - (sum >> 15)| < 2^26 + 12 * 2^26 * 2^15 / 2^15 < 2^31
@@ -267,10 +283,10 @@ __device__ __forceinline__ bool residual_lpc_t(const int32_t (&x)[E + 12], uint3
 #pragma unroll
     for (int t = 1; t <= TAPS; ++t) acc = mad_wide(cf[t], x[12 + j - t], acc);
     const i64 d = (i64)x[12 + j] - (acc >> 15);
-    const bool in = g0 + j < n;
-    if (CHECK && in && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
-    r[j] = in ? (int32_t)d : 0;
+    if (CHECK && g0 + j < n && (d < -2147483648ll || d > 2147483647ll)) ovf = true;
+    r[j] = (int32_t)d;
   }
+  residual_tail<E>(g0, n, r);
   return ovf;
 }
 template <int E, bool CHECK = true>
@@ -340,15 +356,15 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
   uint32_t zmask = 0, umin = 0xFFFFFFFFu, uor = 0u;
 #pragma unroll
   for (int j = 0; j < E; ++j) {
-    const bool in = g0 + j < n;
-    const uint32_t uu = in ? zz32(r[j]) : 0u;
+    const uint32_t uu = zz32(r[j]);  // residuals past the block end are 0
     u[j] = uu;
     S += uu;
     uor |= uu;
-    if (in && uu < umin) umin = uu;
+    umin = uu < umin ? uu : umin;  // a chunk that reaches past the block end reads as "has small values": general walk
     if (uu) lastnz = (int32_t)(g0 + j);
-    if (in && uu == 0u) zmask |= 1u << j;
+    zmask |= (uu == 0u ? 1u : 0u) << j;
   }
+  if (g0 + (uint32_t)E > n) zmask &= g0 < n ? (1u << (n - g0)) - 1u : 0u;  // only samples that exist count as zeros
   pr.zmask = zmask;
   pr.cls = (umin <= 4u ? 1u : 0u) | ((32u - (uint32_t)__clz((int)uor)) << 8);
   uint4* U4 = reinterpret_cast<uint4*>(sm.U());
