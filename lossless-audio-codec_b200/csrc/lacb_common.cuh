@@ -259,6 +259,19 @@ __device__ __forceinline__ u64 warp_sum_u64_full(u64 v) {
   return v;
 }
 
+// 64-bit sums in shared memory fed by native 32-bit atomics (a 64-bit shared-memory atomicAdd is a compare-and-swap
+// loop, and the block totals are hit by all 32 warps at once): word 0 of the slot collects the low 24 bits of every
+// addend, word 1 the rest.  Good for at most 256 addends below 2^56 per slot; a zeroed u64 is an empty slot.
+__device__ __forceinline__ void split_sum_add(u64* slot, u64 v) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(slot);
+  atomicAdd(&w[0], (uint32_t)v & 0xFFFFFFu);
+  atomicAdd(&w[1], (uint32_t)(v >> 24));
+}
+__device__ __forceinline__ u64 split_sum_get(const u64* slot) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(slot);
+  return ((u64)w[1] << 24) + w[0];
+}
+
 // ---------------------------------------------------------------------------
 // Bit-plane population counts.
 //

@@ -529,8 +529,8 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         // registers, so the loop-exit test above is block-uniform without another barrier.  One lane keeps the
         // full record of the best candidate in shared memory for the partition search.
         const u64 stat = mi->stat_bits;
-        const u64 rice = mi->tot_rice, bin = mi->tot_bin;
-        const u64 zr = (cfg.zero_run && has_run) ? mi->tot_zr : rice;  // block/encoder.cpp:343-345
+        const u64 rice = split_sum_get(&mi->tot_rice), bin = split_sum_get(&mi->tot_bin);
+        const u64 zr = (cfg.zero_run && has_run) ? split_sum_get(&mi->tot_zr) : rice;  // block/encoder.cpp:343-345
         const u64 m1 = rice < stat ? rice : stat, m2 = zr < bin ? zr : bin;
         const u64 bb = m1 < m2 ? m1 : m2;
         // strictly fewer bits wins; on a tie the lower predictor type, then the earlier candidate (:352-359) --
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       const u64* Fa = sm.FbAll();
       u64* SelBits = sm.SelBits();
       for (uint32_t sid = 1u + tid; sid < (2u << max_p) - 1u; sid += NT) {
-        const u64 rice = Fa[sid], zr = Fa[STR + sid], bin = Fa[2u * STR + sid];
+        const u64 rice = split_sum_get(&Fa[sid]), zr = split_sum_get(&Fa[STR + sid]), bin = split_sum_get(&Fa[2u * STR + sid]);
         const bool hr = (mi->hasrun_all[sid >> 5] >> (sid & 31u)) & 1u;
         const uint32_t kk = sm.SegK()[sid];
         const u64 sbits = sm.SegStat()[sid];

@@ -1232,9 +1232,9 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
   if (STATEFUL) {
     const u64 r = warp_sum_u64(riceA), z = warp_sum_u64(zrA), b = warp_sum_u64(binA);
     if ((tid & 31u) == 0u) {
-      atomicAdd(&mi->tot_rice, r);
-      atomicAdd(&mi->tot_zr, z);
-      atomicAdd(&mi->tot_bin, b);
+      split_sum_add(&mi->tot_rice, r);
+      if (pr.any4) split_sum_add(&mi->tot_zr, z);  // read only when the block has a run
+      split_sum_add(&mi->tot_bin, b);
     }
     LACB_PH(10);
     const uint32_t any_run = (uint32_t)__syncthreads_or((int)runA);  // also publishes the totals
@@ -1555,9 +1555,9 @@ __device__ __forceinline__ void levels_fused(const ASmem<NT, E>& sm, const Prep<
     }
     const uint32_t lead = per_seg >= 32u ? 31u : per_seg - 1u;
     if ((tid & lead) == 0u) {
-      atomicAdd(&Fa[sid], a);
-      if (pr.any4) atomicAdd(&Fa[STR + sid], b);
-      atomicAdd(&Fa[2u * STR + sid], c);
+      split_sum_add(&Fa[sid], a);
+      if (pr.any4) split_sum_add(&Fa[STR + sid], b);
+      split_sum_add(&Fa[2u * STR + sid], c);
       if (rn) atomicOr(&mi->hasrun_all[sid >> 5], 1u << (sid & 31u));
     }
   }
