@@ -574,7 +574,13 @@ static int enc_slice_begin(lacb_ctx* ctx, const lacb_enc_params* prm, int layout
 static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int layout, const void* pcm_a,
                               const void* pcm_b, uint64_t frames, uint8_t* dst, uint64_t dst_cap,
                               uint8_t** payload_out, uint64_t* payload_bytes, uint32_t* block_bytes, lacb_err* err) {
-  CKR(ensure_kids(ctx));
+  // Three slice contexts in rotation.  With two, the copy of slice i + 1 sat on the stream of slice i - 1 behind that
+  // slice's emit kernel, which cannot start before the analysis of slice i (all SMs, all registers) has finished: the
+  // copy therefore ran AFTER the analysis it was meant to hide under, ~2 ms of idle SMs per large slice.  The third
+  // context's stream is free when slice i + 1 is queued (its last emit only waited for the analysis of slice i - 1).
+  constexpr uint32_t NK = 3u;
+  const uint32_t nkenc = ctx->max_streams >= 2u ? lacb_umin(NK, ctx->max_streams) : NK;  // the caller's cap on slices in flight
+  CKR(ensure_kids(ctx, nkenc));
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
   // Slice plan: the first slices are short (2, 4, 8 waves of jobs) so that the kernels start after a
   // fraction of a millisecond of copying and every later copy hides under the slice before it.
@@ -620,11 +626,11 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
     bb_stage = static_cast<uint32_t*>(ctx->pinned);
   }
   for (uint32_t i = 0; i < ns; ++i) {
-    lacb_ctx* k = ctx->kids[i & 1u];
-    if (i + 1u < ns) {  // next slice: copies and analysis queue up behind slice i - 1 on the other stream
+    lacb_ctx* k = ctx->kids[i % nkenc];
+    if (i + 1u < ns) {  // next slice: its copies run under the analysis of slice i, its analysis queues up behind it
       uint64_t g0, gr;
       slice_range(i + 1u, &g0, &gr);
-      lacb_ctx* kn = ctx->kids[(i + 1u) & 1u];
+      lacb_ctx* kn = ctx->kids[(i + 1u) % nkenc];
       const int rc = enc_slice_begin(kn, prm, layout, pcm_a, pcm_b, g0, gr);
       if (rc != 0) { ctx->err = kn->err; return fail(rc); }
       TRACE("enc slice %u queued", i + 1u);
