@@ -26,6 +26,7 @@ constexpr int FULL_NT = 1024, FULL_E = 16;  // 16384-sample channel-blocks: one 
 constexpr int PROBE_NT = 32, PROBE_E = 8;   // 256-sample stereo probes: one warp
 constexpr size_t kFullSmem = ASmem<FULL_NT, FULL_E>::BYTES;
 constexpr size_t kProbeSmem = ASmem<PROBE_NT, PROBE_E>::BYTES;
+constexpr uint32_t kProbeGang = 32;  // probe warps per CTA
 enum { EV_START = 0, EV_H2D, EV_PREP, EV_STEREO, EV_LPC, EV_ANALYZE, EV_FINAL, EV_EMIT, EV_D2H, EV_COUNT };
 }  // namespace
 
@@ -169,8 +170,15 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
     auto kl = k_levinson<true>;
     LACB_LAUNCH(kl, lacb_umin((nb * 12u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs_p),
                 counts + 1, as<i64>(ctx->acor_p), as<LpcQ>(ctx->lpcq_p));
+    // probe warps run in gangs of kProbeGang per CTA (see k_analyze)
+    static const uint32_t gang = [] {  // experiment knob, 1..32 sub-blocks per CTA
+      const char* e = getenv("LACB_PROBE_GANG");
+      const int v = e ? atoi(e) : 0;
+      return (uint32_t)(v >= 1 && v <= 32 ? v : (int)kProbeGang);
+    }();
+    const uint32_t ggrid = lacb_umin((nb * 12u + gang - 1u) / gang, (uint32_t)ctx->sms * (32u / gang));
     auto kz = k_analyze<PROBE_NT, PROBE_E, true>;
-    LACB_LAUNCH(kz, pgrid, PROBE_NT, kProbeSmem, st, src, cfg, as<uint32_t>(ctx->jobs_p),
+    LACB_LAUNCH(kz, ggrid, PROBE_NT * gang, kProbeSmem * gang, st, src, cfg, as<uint32_t>(ctx->jobs_p),
                 counts + 1, as<LpcQ>(ctx->lpcq_p), (ChanRec*)nullptr, as<uint32_t>(ctx->probe_bytes));
     auto kd = k_decide_probes;
     LACB_LAUNCH(kd, lacb_umin((nb + 255u) / 256u, (uint32_t)ctx->sms), 256, 0, st, cfg, as<uint32_t>(ctx->flags),
@@ -186,8 +194,8 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
     auto kb = k_build_jobs<false>;
     LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs), counts);
     const uint32_t fgrid = lacb_umin(nb * 4u, (uint32_t)ctx->sms);
-    auto ka = k_autocorr<FULL_NT, FULL_E, false>;
-    LACB_LAUNCH(ka, fgrid, FULL_NT, FULL_NT * FULL_E * 4, st, src, as<uint32_t>(ctx->jobs), counts,
+    auto ka = k_autocorr_stream<256>;
+    LACB_LAUNCH(ka, lacb_umin(nb * 4u, (uint32_t)ctx->sms * 2u), 256, 0, st, src, as<uint32_t>(ctx->jobs), counts,
                 as<i64>(ctx->acor));
     auto kl = k_levinson<false>;
     LACB_LAUNCH(kl, lacb_umin((nb * 4u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs),
@@ -332,10 +340,10 @@ int lacb_create(int device, lacb_ctx** out) {
   for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&ctx->ev[i]);
   cudaFuncSetAttribute(k_analyze<FULL_NT, FULL_E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)ASmem<FULL_NT, FULL_E>::BYTES);
+  cudaFuncSetAttribute(k_analyze<PROBE_NT, PROBE_E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(kProbeSmem * 32));
   cudaFuncSetAttribute(k_emit<FULL_NT, FULL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)ASmem<FULL_NT, FULL_E>::BYTES);
-  cudaFuncSetAttribute(k_autocorr<FULL_NT, FULL_E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       FULL_NT * FULL_E * 4);
   if (cudaGetLastError() != cudaSuccess) {
     lacb_destroy(ctx);
     return LACB_ECUDA;
@@ -863,9 +871,8 @@ int lacb_lpc_analyze(lacb_ctx* ctx, const int32_t* pcm, uint32_t n, int order, i
   CK(cudaMemcpyAsync(ctx->jobs.p, &one[0], 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->counts.p, &one[1], 4, cudaMemcpyHostToDevice, st));
   PcmSrc src{as<int32_t>(ctx->planeL), nullptr, n};
-  auto ka = k_autocorr<FULL_NT, FULL_E, false>;
-  LACB_LAUNCH(ka, 1, FULL_NT, FULL_NT * FULL_E * 4, st, src, as<uint32_t>(ctx->jobs), as<uint32_t>(ctx->counts),
-              as<i64>(ctx->acor));
+  auto ka = k_autocorr_stream<256>;
+  LACB_LAUNCH(ka, 1, 256, 0, st, src, as<uint32_t>(ctx->jobs), as<uint32_t>(ctx->counts), as<i64>(ctx->acor));
   auto kl = k_levinson<false>;
   LACB_LAUNCH(kl, 1, 64, 0, st, src, as<uint32_t>(ctx->jobs), as<uint32_t>(ctx->counts), as<i64>(ctx->acor),
               as<LpcQ>(ctx->lpcq));

@@ -127,9 +127,28 @@ __device__ __forceinline__ u64 rice_cost(uint32_t u, uint32_t k) {
 // ---------------------------------------------------------------------------
 // Block-wide primitives.  `scratch` holds 33 entries per scanned value; every call
 // ends with a barrier so the scratch can be reused immediately.
+// Sub-blocks.  A 256-sample stereo probe is analysed by ONE warp (NT == 32), and many probe warps share a CTA so that
+// they can be kept in step through the code (k_analyze): inside NT == 32 code the "thread index" is the lane, a "block
+// barrier" is a warp barrier and a "block vote" a warp vote.  Every other NT is a real CTA.
+template <int NT>
+__device__ __forceinline__ uint32_t blk_tid() { return NT == 32 ? (threadIdx.x & 31u) : threadIdx.x; }
+template <int NT>
+__device__ __forceinline__ void blk_sync() {
+  if (NT == 32) __syncwarp();
+  else __syncthreads();
+}
+template <int NT>
+__device__ __forceinline__ int blk_sync_or(int p) {
+  if (NT == 32) return __any_sync(kFull, p);
+  return __syncthreads_or(p);
+}
+#define LACB_TID (::lacb::blk_tid<NT>())
+#define LACB_SYNC() ::lacb::blk_sync<NT>()
+#define LACB_SYNC_OR(p) ::lacb::blk_sync_or<NT>(p)
+
 template <int NT>
 __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64* scratch, u64* total) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t tid = LACB_TID, lane = tid & 31u, w = tid >> 5;
   constexpr int NW = (NT + 31) / 32;
   u64 inc = v;
 #pragma unroll
@@ -142,7 +161,7 @@ __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64* scratch, u64* tot
     return inc - v;
   }
   if (lane == 31u) scratch[w] = inc;
-  __syncthreads();
+  LACB_SYNC();
   u64 ws = (lane < (uint32_t)NW) ? scratch[lane] : 0ull;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -151,14 +170,14 @@ __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64* scratch, u64* tot
   }
   const u64 wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
   const u64 tot = __shfl_sync(kFull, ws, NW - 1);
-  __syncthreads();
+  LACB_SYNC();
   if (total) *total = tot;
   return (w ? wprev : 0ull) + inc - v;
 }
 
 template <int NT>
 __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* scratch, uint32_t* total) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t tid = LACB_TID, lane = tid & 31u, w = tid >> 5;
   constexpr int NW = (NT + 31) / 32;
   uint32_t inc = v;
 #pragma unroll
@@ -171,7 +190,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* sc
     return inc - v;
   }
   if (lane == 31u) scratch[w] = inc;
-  __syncthreads();
+  LACB_SYNC();
   uint32_t ws = (lane < (uint32_t)NW) ? scratch[lane] : 0u;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -180,7 +199,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* sc
   }
   const uint32_t wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
   const uint32_t tot = __shfl_sync(kFull, ws, NW - 1);
-  __syncthreads();
+  LACB_SYNC();
   if (total) *total = tot;
   return (w ? wprev : 0u) + inc - v;
 }
@@ -192,7 +211,7 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t* sc
 template <int NT, bool TRAIL>
 __device__ __forceinline__ void block_scan_sum_max(u64 v, int32_t m, u64* scratch, u64* ex_sum, u64* total,
                                                    int32_t* ex_max) {
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+  const uint32_t tid = LACB_TID, lane = tid & 31u, w = tid >> 5;
   constexpr int NW = (NT + 31) / 32;
   u64 inc = v;
   int32_t im = m;
@@ -211,7 +230,7 @@ __device__ __forceinline__ void block_scan_sum_max(u64 v, int32_t m, u64* scratc
     *total = __shfl_sync(kFull, inc, 31);
     *ex_sum = inc - v;
     *ex_max = exm;
-    __syncthreads();  // callers rely on one barrier inside the scan
+    LACB_SYNC();  // callers rely on one barrier inside the scan
     return;
   }
   int32_t* smax = reinterpret_cast<int32_t*>(scratch + 32);
@@ -220,7 +239,7 @@ __device__ __forceinline__ void block_scan_sum_max(u64 v, int32_t m, u64* scratc
     smax[w] = im;
   }
   LACB_PH(2);
-  __syncthreads();
+  LACB_SYNC();
   LACB_PH(3);
   u64 ws = (lane < (uint32_t)NW) ? scratch[lane] : 0ull;
   int32_t wm = (lane < (uint32_t)NW) ? smax[lane] : -1;
@@ -236,7 +255,7 @@ __device__ __forceinline__ void block_scan_sum_max(u64 v, int32_t m, u64* scratc
   const u64 wprev = __shfl_sync(kFull, ws, (int)((w + 31u) & 31u));
   const int32_t wmprev = __shfl_sync(kFull, wm, (int)((w + 31u) & 31u));
   *total = __shfl_sync(kFull, ws, NW - 1);
-  if (TRAIL) __syncthreads();
+  if (TRAIL) LACB_SYNC();
   *ex_sum = (w ? wprev : 0ull) + inc - v;
   if (w && wmprev > exm) exm = wmprev;
   *ex_max = exm;

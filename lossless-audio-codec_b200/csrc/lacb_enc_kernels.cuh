@@ -168,6 +168,84 @@ __device__ __forceinline__ u64 proxy_bits(u64 sum, u64 count) {
   while (k < 31u && (1ull << k) < mean) ++k;
   return sat_add(sum >> k, count * (u64)(k + 1u));
 }
+// The twelve sums of one block.  NARROW: every |sample| <= 2^24 (all 16 / 24-bit audio), so a term is below 2^27
+// and the arithmetic fits 32 bits; a thread takes four consecutive frames per step (128-bit plane loads when the block
+// is aligned) and folds its 32-bit partial sums into the 64-bit ones every fourth step (16 terms < 2^31).  The wide
+// form is the reference's int64 arithmetic sample by sample.  Both return the OR of the sample magnitudes seen.
+template <bool NARROW>
+__device__ __forceinline__ uint32_t stereo_proxy_sums(const PcmSrc& src, u64 start, uint32_t n, u64 (&s)[12]) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t mag = 0u;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) s[i] = 0ull;
+  if (NARROW) {
+    const bool vec = ((reinterpret_cast<uint64_t>(src.L + start) | reinterpret_cast<uint64_t>(src.R + start)) & 15ull) == 0ull;
+    uint32_t a[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a[i] = 0u;
+    uint32_t step = 0u;
+    for (uint32_t q = tid; q * 4u < n; q += blockDim.x, ++step) {
+      int32_t l[5], r[5];  // [0] = the frame before the quad (zero before the block start)
+      const uint32_t i0 = q * 4u;
+      l[0] = i0 ? src.L[start + i0 - 1u] : 0;
+      r[0] = i0 ? src.R[start + i0 - 1u] : 0;
+      if (vec && i0 + 4u <= n) {
+        const int4 vl = reinterpret_cast<const int4*>(src.L + start)[q], vr = reinterpret_cast<const int4*>(src.R + start)[q];
+        l[1] = vl.x; l[2] = vl.y; l[3] = vl.z; l[4] = vl.w;
+        r[1] = vr.x; r[2] = vr.y; r[3] = vr.z; r[4] = vr.w;
+      } else {
+#pragma unroll
+        for (uint32_t m = 0; m < 4u; ++m) {
+          const bool in = i0 + m < n;
+          l[1 + m] = in ? src.L[start + i0 + m] : 0;
+          r[1 + m] = in ? src.R[start + i0 + m] : 0;
+        }
+      }
+      mag |= (uint32_t)(l[0] ^ (l[0] >> 31)) | (uint32_t)(r[0] ^ (r[0] >> 31));
+#pragma unroll
+      for (int m = 1; m <= 4; ++m) {
+        mag |= (uint32_t)(l[m] ^ (l[m] >> 31)) | (uint32_t)(r[m] ^ (r[m] >> 31));
+        if (i0 + (uint32_t)m - 1u >= n) continue;  // past the block end (only in the last quad)
+        const int32_t v[4] = {l[m], r[m], (l[m] + r[m]) >> 1, l[m] - r[m]};
+        const int32_t pv[4] = {l[m - 1], r[m - 1], (l[m - 1] + r[m - 1]) >> 1, l[m - 1] - r[m - 1]};
+        const bool first = i0 + (uint32_t)m - 1u == 0u;  // the block's first sample: no neighbour, all three forms are raw
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t raw = zz32(v[c]);
+          a[c] += raw;
+          a[4 + c] += first ? raw : zz32(v[c] - pv[c]);
+          a[8 + c] += first ? raw : zz32(v[c] + pv[c]);
+        }
+      }
+      if ((step & 3u) == 3u) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { s[i] += a[i]; a[i] = 0u; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] += a[i];
+    return mag;
+  }
+  for (uint32_t i = tid; i < n; i += blockDim.x) {
+    i64 v[4], pv[4];
+    const i64 l = src.L[start + i], r = src.R[start + i];
+    v[0] = l; v[1] = r; v[2] = (l + r) >> 1; v[3] = l - r;
+    if (i > 0u) {
+      const i64 pl = src.L[start + i - 1u], prr = src.R[start + i - 1u];
+      pv[0] = pl; pv[1] = prr; pv[2] = (pl + prr) >> 1; pv[3] = pl - prr;
+    } else {
+      pv[0] = pv[1] = pv[2] = pv[3] = 0;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      // per-sample terms are < 2^35, so plain adds cannot wrap within a block
+      s[c] += zz64(v[c]);
+      s[4 + c] += (i == 0u) ? zz64(v[c]) : zz64(v[c] - pv[c]);
+      s[8 + c] += (i == 0u) ? zz64(v[c]) : zz64(v[c] + pv[c]);
+    }
+  }
+  return 0u;
+}
 __global__ void __launch_bounds__(256) k_stereo_proxy(PcmSrc src, EncCfg cfg, uint32_t* blk_flags) {
   __shared__ u64 acc[12];
   const uint32_t tid = threadIdx.x;
@@ -175,28 +253,11 @@ __global__ void __launch_bounds__(256) k_stereo_proxy(PcmSrc src, EncCfg cfg, ui
     const uint32_t n = block_len(src.frames, b);
     const u64 start = (u64)b * kMaxBlock;
     if (tid < 12u) acc[tid] = 0ull;
-    __syncthreads();
     u64 s[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = 0ull;
-    for (uint32_t i = tid; i < n; i += blockDim.x) {
-      i64 v[4], pv[4];
-      const i64 l = src.L[start + i], r = src.R[start + i];
-      v[0] = l; v[1] = r; v[2] = (l + r) >> 1; v[3] = l - r;
-      if (i > 0u) {
-        const i64 pl = src.L[start + i - 1u], prr = src.R[start + i - 1u];
-        pv[0] = pl; pv[1] = prr; pv[2] = (pl + prr) >> 1; pv[3] = pl - prr;
-      } else {
-        pv[0] = pv[1] = pv[2] = pv[3] = 0;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        // per-sample terms are < 2^35, so plain adds cannot wrap within a block
-        s[c] += zz64(v[c]);
-        s[4 + c] += (i == 0u) ? zz64(v[c]) : zz64(v[c] - pv[c]);
-        s[8 + c] += (i == 0u) ? zz64(v[c]) : zz64(v[c] + pv[c]);
-      }
-    }
+    // the 32-bit form first; a block that holds a sample beyond +-2^24 (planar int32 input that was not validated
+    // against a bit depth) is summed again in 64 bits -- the vote is also the barrier behind the zeroing of acc
+    const uint32_t mag = stereo_proxy_sums<true>(src, start, n, s);
+    if (__syncthreads_or((int)((mag >> 24) != 0u))) stereo_proxy_sums<false>(src, start, n, s);
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
       const u64 t = warp_sum_u64(s[i]);
@@ -309,6 +370,88 @@ __global__ void __launch_bounds__(NT) k_autocorr(PcmSrc src, const uint32_t* job
   }
 }
 
+// K5 for whole channel-blocks, streaming form.  The sums are exact wrapping int64, so any summation order gives the
+// reference's value; nothing has to be staged: a thread reads its 16 samples and the 12 before them straight from the
+// planes (the halo is its neighbour's own chunk, an L1 / L2 hit), several small CTAs share an SM so that the loads of
+// one hide under the multiply-adds of the others, and a job costs one reduction however long the block is.  (The
+// one-CTA-per-SM form above waits for its 64 KB block, computes, reduces: 0.52 ms for 7032 channel-blocks, six times
+// its arithmetic.)
+template <int NT>
+__global__ void __launch_bounds__(NT, 2) k_autocorr_stream(PcmSrc src, const uint32_t* jobs, const uint32_t* job_count,
+                                                           i64* acor) {
+  constexpr int E = 16;
+  __shared__ u64 red[NT / 32][13];
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nj = *job_count;
+  for (uint32_t ji = blockIdx.x; ji < nj; ji += gridDim.x) {
+    const uint32_t slot = jobs[ji];
+    JobDesc jd;
+    job_desc<false>(src, slot, jd);
+    const uint32_t n = jd.n;
+    const int kind = jd.kind;
+    const int32_t* pa = (kind == 1 ? src.R : src.L) + jd.start;
+    const int32_t* pb = (kind >= 2 ? src.R : src.L) + jd.start;  // second operand of mid / side
+    const bool vec_ok = ((reinterpret_cast<uint64_t>(pa) | reinterpret_cast<uint64_t>(pb)) & 15ull) == 0ull;
+    u64 s[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) s[k] = 0ull;
+    for (uint32_t c0 = tid; c0 * (uint32_t)E < n; c0 += NT) {
+      int4 a[E / 4 + 3], b[E / 4 + 3];
+      const int q0 = (int)c0 * (E / 4);
+#pragma unroll
+      for (int c = -3; c < E / 4; ++c) {
+        const int q = q0 + c;
+        int4 va = make_int4(0, 0, 0, 0), vb = make_int4(0, 0, 0, 0);
+        if (q >= 0 && (uint32_t)q * 4u < n) {
+          if (vec_ok && (uint32_t)q * 4u + 4u <= n) {
+            va = reinterpret_cast<const int4*>(pa)[q];
+            if (kind >= 2) vb = reinterpret_cast<const int4*>(pb)[q];
+          } else {  // unaligned planes, or the quad straddling the end of the block
+            int32_t t[4] = {0, 0, 0, 0}, w[4] = {0, 0, 0, 0};
+            for (uint32_t m = 0; m < 4u; ++m)
+              if ((uint32_t)q * 4u + m < n) {
+                t[m] = pa[(uint32_t)q * 4u + m];
+                if (kind >= 2) w[m] = pb[(uint32_t)q * 4u + m];
+              }
+            va = make_int4(t[0], t[1], t[2], t[3]);
+            vb = make_int4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        a[c + 3] = va;
+        b[c + 3] = vb;
+      }
+      int32_t x[E + 12];
+#pragma unroll
+      for (int c = 0; c < E / 4 + 3; ++c) {
+        // kind 0 / 1: the plane itself; 2: mid, 3: side (combine_sample; a zero quad stays zero)
+        const int k2 = kind >= 2 ? kind : 0;
+        x[4 * c + 0] = combine_sample(k2, a[c].x, b[c].x);
+        x[4 * c + 1] = combine_sample(k2, a[c].y, b[c].y);
+        x[4 * c + 2] = combine_sample(k2, a[c].z, b[c].z);
+        x[4 * c + 3] = combine_sample(k2, a[c].w, b[c].w);
+      }
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+#pragma unroll
+        for (int k = 0; k < 13; ++k) s[k] = (u64)mad_wide(x[12 + j], x[12 + j - k], (i64)s[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 13; ++k) {
+      const u64 t = warp_sum_u64_full(s[k]);
+      if ((tid & 31u) == 0u) red[tid >> 5][k] = t;
+    }
+    __syncthreads();
+    if (tid < 13u) {
+      u64 t = 0ull;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) t += red[w][tid];
+      acor[(size_t)slot * 13u + tid] = (i64)t;
+    }
+    __syncthreads();
+  }
+}
+
 // K6: Levinson-Durbin + Q15 quantisation, one thread per job (lpc.cpp:98-186).
 template <bool PROBE>
 __global__ void k_levinson(PcmSrc src, const uint32_t* jobs, const uint32_t* job_count, const i64* acor, LpcQ* lpcq) {
@@ -342,13 +485,13 @@ __global__ void k_levinson(PcmSrc src, const uint32_t* jobs, const uint32_t* job
 template <int NT, int E>
 __device__ __forceinline__ u64 block_sum_u64(const ASmem<NT, E>& sm, u64 v) {
   AMisc* mi = sm.Misc();
-  if (threadIdx.x == 0) mi->red64 = 0ull;
-  __syncthreads();
+  if (LACB_TID == 0) mi->red64 = 0ull;
+  LACB_SYNC();
   const u64 t = warp_sum_u64(v);
-  if ((threadIdx.x & 31u) == 0u && t) atomicAdd(&mi->red64, t);
-  __syncthreads();
+  if ((LACB_TID & 31u) == 0u && t) atomicAdd(&mi->red64, t);
+  LACB_SYNC();
   const u64 r = mi->red64;
-  __syncthreads();
+  LACB_SYNC();
   return r;
 }
 
@@ -366,15 +509,29 @@ __device__ __forceinline__ bool compute_residual(const int32_t (&x)[E + 12], uin
   return residual_lpc<E, false>(x, g0, n, coef, (int)taps, r);  // the analysis already settled the taps
 }
 
+//
+// Gangs (NT == 32, the 256-sample stereo probes).  A probe is analysed by one warp, and its search is this same code --
+// hundreds of KB of instructions.  As independent one-warp CTAs the 32 resident probes of an SM each sat somewhere else
+// in that code and the kernel starved on instruction fetches (ncu: 37 warp-cycles of "no instruction" per issued
+// instruction, issue slots 16 % busy).  So the probe warps of an SM form one CTA (a gang, blockDim.x / 32 sub-blocks
+// with their own slice of the dynamic shared memory) and are put back in step by CTA barriers at the top of every job,
+// every candidate evaluation and every partition level: at any moment they all run the same phase and fetch the same
+// code.  Inside a sub-block "thread", "barrier" and "vote" mean lane, warp barrier and warp vote (blk_tid / blk_sync).
+// The last, partly filled row of jobs is completed with copies of the last job (same result, written twice), so every
+// sub-block passes the same barriers.
 template <int NT, int E, bool PROBE>
-__global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
+__global__ void __launch_bounds__(NT == 32 ? 1024 : NT, 1) k_analyze(PcmSrc src, EncCfg cfg, const uint32_t* jobs, const uint32_t* job_count,
                                                 const LpcQ* lpcq, ChanRec* recs, uint32_t* probe_bytes) {
   LACB_DYN_SMEM(unsigned char, smraw);
-  ASmem<NT, E> sm{smraw};
+  constexpr bool GANG = NT == 32;
+  const uint32_t gang = GANG ? blockDim.x >> 5 : 1u, sub = GANG ? threadIdx.x >> 5 : 0u;
+  ASmem<NT, E> sm{smraw + (size_t)sub * ASmem<NT, E>::BYTES};
   AMisc* mi = sm.Misc();
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   const uint32_t nj = *job_count;
-  for (uint32_t ji = blockIdx.x; ji < nj; ji += gridDim.x) {
+  for (uint32_t jrow = blockIdx.x * gang; jrow < nj; jrow += gridDim.x * gang) {
+    const uint32_t ji = jrow + sub < nj ? jrow + sub : nj - 1u;
+    if (GANG) __syncthreads();
     const uint32_t slot = jobs[ji];
     JobDesc jd;
     job_desc<PROBE>(src, slot, jd);
@@ -383,7 +540,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     if (tid < 11u) mi->cand_lb[tid] = 0u;  // ordered before the pre-pass by the barrier of the vote below
     // block-uniform: some sample needs more than 26 magnitude bits (never true for 16 / 24-bit audio);
     // only then can an LPC residual leave int32 (lpc.cpp:38-61) and the fallback orders matter
-    const bool xbig = __syncthreads_or((int)((load_block<NT, E>(sm, src, jd.kind, jd.start, n) >> 26) != 0u)) != 0;
+    const bool xbig = LACB_SYNC_OR((int)((load_block<NT, E>(sm, src, jd.kind, jd.start, n) >> 26) != 0u)) != 0;
     LACB_PH(0);
     const uint32_t max_valid = n > 1u ? (n - 1u < 32u ? n - 1u : 32u) : 0u;
     const LpcQ* lq = lpcq + slot;
@@ -448,7 +605,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
           publish(ci, bound(r));
         }
       }
-      __syncthreads();
+      LACB_SYNC();
     }
     if (tid < 11u) {
       // rank of candidate `tid` among the existing ones by (bound, index); without the pre-pass all bounds are 0
@@ -467,14 +624,25 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     }
     if (tid == 0u) mi->best.have = 0u;
     if (tid == 0u) mi->hq_kb_n = 0u;
-    __syncthreads();
+    LACB_SYNC();
     const uint32_t n_cand = mi->cand_n;
     bool have_best = false;
     u64 best_bits = 0ull;
     uint32_t best_ci = 0u;
-    for (uint32_t idx = 0; idx < n_cand; ++idx) {
-      const uint32_t ci = mi->cand_order[idx];
-      if (have_best && (u64)mi->cand_lb[ci] > best_bits) break;  // this one and all later ones are out
+    bool cand_done = false;
+    for (uint32_t idx = 0;; ++idx) {
+      uint32_t ci = 0u;
+      if (idx >= n_cand) cand_done = true;
+      if (!cand_done) {
+        ci = mi->cand_order[idx];
+        if (have_best && (u64)mi->cand_lb[ci] > best_bits) cand_done = true;  // this one and all later ones are out
+      }
+      if (GANG) {  // the gang goes on while any of its probes has a candidate left; the others wait here
+        if (!__syncthreads_or((int)!cand_done)) break;
+        if (cand_done) continue;
+      } else if (cand_done) {
+        break;
+      }
       int32_t r[E];
       uint32_t type, order, taps = 0u;
       {
@@ -503,7 +671,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
           }
           while (attempt > 0u) {
             const bool ovf = residual_lpc<E, true>(x, g0, n, lq->coef[c], (int)attempt, r);
-            if (!__syncthreads_or((int)ovf)) {
+            if (!LACB_SYNC_OR((int)ovf)) {
               taps = attempt;
               break;
             }
@@ -551,9 +719,10 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       }
     }
     LACB_PH(1);
-    __syncthreads();
+    LACB_SYNC();
     LACB_PH_BASE(PROBE ? -1 : 20);
     const BestCand best = mi->best;
+    if (GANG) __syncthreads();
 
     // winner residual again, with the full prefix structures for the partition search
     const int16_t* wcoef = best.type == PRED_LPC ? lq->coef[best.ci - 6u] : nullptr;
@@ -593,7 +762,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       sm.SegK()[sid] = (uint16_t)(ki | (ks << 8));
     }
     LACB_PH(12);
-    __syncthreads();
+    LACB_SYNC();
     LACB_PH(13);
 
     // base (p = 0) mode, block/encoder.cpp:432-484
@@ -608,7 +777,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
     uint32_t best_p = 0u;
     if (tid == 0u) sm.SelMK()[0] = (uint8_t)((base_mode << 5) | base_k);
     if (!PROBE && tid < 9u) recs[slot].lvl_bits[tid] = tid ? 0u : (uint32_t)best_total;
-    __syncthreads();
+    LACB_SYNC();
 
     // partition search, block/encoder.cpp:486-545
     const bool fused = (NT >= 64) && n == (uint32_t)(NT * E) && max_p >= 1u;
@@ -631,7 +800,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         sm.SelMK()[sid] = (uint8_t)((mode << 5) | k);
         SelBits[sid] = bits;
       }
-      __syncthreads();
+      LACB_SYNC();
       const uint32_t warp = tid >> 5;
       if (warp >= 1u && warp <= max_p) {  // warp p adds up level p
         const uint32_t cnt = 1u << warp;
@@ -642,7 +811,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         total += (8ull - (total & 7ull)) & 7ull;
         if ((tid & 31u) == 0u) mi->lvl_total[warp] = total;
       }
-      __syncthreads();
+      LACB_SYNC();
       for (uint32_t p = 1u; p <= max_p; ++p) {
         const u64 total = mi->lvl_total[p];
         if (!PROBE && tid == 0u) recs[slot].lvl_bits[p] = (uint32_t)total;
@@ -656,6 +825,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
       LACB_PH(16);
     } else
     for (uint32_t p = 1u; p <= max_p; ++p) {
+      if (GANG) __syncthreads();  // max_p is the same for every probe (256 samples, one configuration)
       const bool sums = cost_pass<NT, E, false>(sm, pr, n, p, 0u) != 0u;  // Fb: per-segment sums or prefixes
       const uint32_t cnt = 1u << p;
       const u64* Fb = sm.Fb();
@@ -676,7 +846,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         sm.SelMK()[sid] = (uint8_t)((mode << 5) | k);
         SelBits[s] = bits;
       }
-      __syncthreads();
+      LACB_SYNC();
       // every warp adds up the (at most 256) segment costs itself: one barrier instead of a block reduction
       u64 part_sum = 0ull;
       for (uint32_t s = tid & 31u; s < cnt; s += 32u) part_sum += SelBits[s];
@@ -699,6 +869,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
                               : best.order;  // block/encoder.cpp:421-423
     const uint32_t nparts = 1u << best_p;
     u64 tok_bits = 0ull;
+    if (GANG) __syncthreads();
     if (fused && best_p >= 1u) {
       // full block, partitioned: the register walk of the level sweep, no K plane, no barrier
       chunk_walk_stateless<NT, E, true>(sm, pr, n, best_p,
@@ -749,7 +920,7 @@ __global__ void __launch_bounds__(NT, (NT == 32 ? 32 : 1)) k_analyze(PcmSrc src,
         rec->est_stat = best.stat;
       }
     }
-    __syncthreads();
+    LACB_SYNC();
   }
 }
 

@@ -161,7 +161,7 @@ __device__ __forceinline__ uint32_t load_block(const ASmem<NT, E>& sm, const Pcm
     int4 a[Q], b[Q];
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
-      const uint32_t q = (uint32_t)k * NT + threadIdx.x;
+      const uint32_t q = (uint32_t)k * NT + LACB_TID;
       a[k] = make_int4(0, 0, 0, 0);
       b[k] = make_int4(0, 0, 0, 0);
       if (q * 4u + 4u <= n) {
@@ -180,7 +180,7 @@ __device__ __forceinline__ uint32_t load_block(const ASmem<NT, E>& sm, const Pcm
     }
 #pragma unroll
     for (int k = 0; k < Q; ++k) {
-      const uint32_t q = (uint32_t)k * NT + threadIdx.x;
+      const uint32_t q = (uint32_t)k * NT + LACB_TID;
       int4 v;
       v.x = combine_sample(kind, a[k].x, b[k].x);
       v.y = combine_sample(kind, a[k].y, b[k].y);
@@ -192,7 +192,7 @@ __device__ __forceinline__ uint32_t load_block(const ASmem<NT, E>& sm, const Pcm
     }
     return mag;
   }
-  for (uint32_t i = threadIdx.x; i < ASmem<NT, E>::CAP; i += NT) {
+  for (uint32_t i = LACB_TID; i < ASmem<NT, E>::CAP; i += NT) {
     int32_t v = 0;
     if (i < n) v = load_sample(src, kind, start + i);
     mag |= (uint32_t)(v ^ (v >> 31));
@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t load_block(const ASmem<NT, E>& sm, const Pcm
 template <int NT, int E>
 __device__ __forceinline__ void load_items(const ASmem<NT, E>& sm, int32_t (&x)[E + 12]) {
   const int4* X4 = reinterpret_cast<const int4*>(sm.X());
-  const int q0 = (int)threadIdx.x * (E / 4);
+  const int q0 = (int)LACB_TID * (E / 4);
 #pragma unroll
   for (int c = -3; c < E / 4; ++c) {
     int4 v = make_int4(0, 0, 0, 0);
@@ -336,7 +336,7 @@ __device__ __forceinline__ void load_u(const ASmem<NT, E>& sm, uint32_t (&u)[E])
   const uint4* U4 = reinterpret_cast<const uint4*>(sm.U());
 #pragma unroll
   for (int c = 0; c < E / 4; ++c) {
-    const uint4 v = U4[swz_chunk(threadIdx.x * (E / 4) + c)];
+    const uint4 v = U4[swz_chunk(LACB_TID * (E / 4) + c)];
     u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
   }
 }
@@ -348,7 +348,7 @@ __device__ __forceinline__ uint32_t zero_lookahead(const ASmem<NT, E>& sm, const
 // no bit-plane counts and no lower bound.
 template <int NT, int E, bool FULL, bool LIGHT = false>
 __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&r)[E], uint32_t n, Prep<NT, E>& pr) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   AMisc* mi = sm.Misc();
   uint32_t u[E];
   u64 S = 0;
@@ -415,7 +415,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
 #pragma unroll
         for (int w = 0; w < 8; ++w) wtot[wid * 8u + w] = inc[w];
       }
-      __syncthreads();
+      LACB_SYNC();
     }
     PlaneCounts ex;
 #pragma unroll
@@ -436,7 +436,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
       if (tid == 0) Cp[NT].w[w] = total;
     }
     Cp[tid] = ex;
-    __syncthreads();
+    LACB_SYNC();
   } else {
     const bool first = g0 < 256u;
 #pragma unroll
@@ -456,7 +456,7 @@ __device__ __forceinline__ void prepare(const ASmem<NT, E>& sm, const int32_t (&
     const uint32_t zm = zero_lookahead(sm, pr, n);
     const uint32_t r4 = zm & (zm >> 1) & (zm >> 2) & (zm >> 3) & ((1u << E) - 1u);
     LACB_PH(4);
-    pr.any4 = (uint32_t)__syncthreads_or((int)(r4 != 0u));
+    pr.any4 = (uint32_t)LACB_SYNC_OR((int)(r4 != 0u));
     LACB_PH(5);
   }
 }
@@ -518,7 +518,7 @@ __device__ __forceinline__ SegGeom seg_geom(uint32_t g0, uint32_t n, uint32_t p)
 template <int NT, int E, bool STATEFUL, bool FAST, bool DEFER>
 __device__ __forceinline__ bool k_series_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                                 const SegGeom& sg, uint32_t (&kpk)[E / 4], uint32_t& flg_out) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   uint32_t u[E];
   load_u<NT, E>(sm, u);
   const u64 PaA = STATEFUL ? 0ull : sm.SegP()[sg.sidA];
@@ -605,7 +605,7 @@ __device__ __forceinline__ bool k_series_thread(const ASmem<NT, E>& sm, const Pr
 // of the chunk to the K plane and, for the stateful model, its flag word.
 template <int NT, int E, bool STATEFUL>
 __device__ __forceinline__ void k_base_pair(const ASmem<NT, E>& sm, uint32_t tA, uint32_t tB, uint32_t n, uint32_t p) {
-  const uint32_t lane = threadIdx.x & 31u, j = lane & 15u;
+  const uint32_t lane = LACB_TID & 31u, j = lane & 15u;
   const uint32_t t = lane < 16u ? tA : tB;
   const bool live = t < (uint32_t)NT;
   const uint32_t tc = live ? t : 0u;
@@ -654,7 +654,7 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t w) { return ((w + 0x7
 template <int NT, int E, bool SLOW>
 __device__ __forceinline__ bool k_bias_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t flg,
                                               uint32_t (&kpk)[E / 4]) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   const uint32_t* Flg = sm.Flg();
   constexpr int D = (int)kMicroWin / E;       // threads spanned by the 96-sample micro window
   constexpr int DW = (int)kDriftWin / E;      // threads spanned by the 256-sample drift window
@@ -830,7 +830,7 @@ __device__ __forceinline__ bool k_bias_thread(const ASmem<NT, E>& sm, const Prep
 template <int NT, int E>
 __device__ __forceinline__ void k_bias_pair(const ASmem<NT, E>& sm, uint32_t tA, uint32_t tB) {
   constexpr uint32_t D = kMicroWin / E, DW = kDriftWin / E;
-  const uint32_t lane = threadIdx.x & 31u, j = lane & 15u;
+  const uint32_t lane = LACB_TID & 31u, j = lane & 15u;
   const uint32_t t = lane < 16u ? tA : tB;
   const bool live = t < (uint32_t)NT;
   const uint32_t tc = live ? t : 0u;  // idle half-warps follow along on chunk 0 and drop the result
@@ -894,7 +894,7 @@ __device__ __forceinline__ void block_static_k(const ASmem<NT, E>& sm, uint32_t 
   u64 sb;
   const uint32_t ki = warp_best_static_k(mi->p_first, mi->cnt_first, n < 256u ? n : 256u, 12, nullptr);
   const uint32_t ks = warp_best_static_k(mi->u_total, mi->cnt_tot, n, 15, &sb);
-  if ((threadIdx.x & 31u) == 0u) {
+  if ((LACB_TID & 31u) == 0u) {
     mi->k_init = ki;
     mi->k_stat = ks;
     mi->stat_bits = sb;
@@ -905,13 +905,13 @@ __device__ __forceinline__ void block_static_k(const ASmem<NT, E>& sm, uint32_t 
 // (one shared-memory atomic per warp).  Warp collective.
 template <int NT, int E>
 __device__ __forceinline__ void queue_push(const ASmem<NT, E>& sm, uint32_t* counter, bool want) {
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = LACB_TID & 31u;
   const uint32_t m = __ballot_sync(kFull, want);
   if (!m) return;
   uint32_t base = 0u;
   if (lane == 0u) base = atomicAdd(counter, (uint32_t)__popc(m));
   base = __shfl_sync(kFull, base, 0);
-  if (want) sm.HardQ()[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+  if (want) sm.HardQ()[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint16_t)LACB_TID;
 }
 
 // The k series of one level, left in the K plane (ends with a barrier).
@@ -931,7 +931,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
                                          const SegGeom& sg, uint32_t p = 0u) {
   constexpr bool COOP = (NT >= 64) && (E == 16);
   constexpr uint32_t NW = NT / 32;
-  const uint32_t tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t tid = LACB_TID, warp = tid >> 5;
   AMisc* mi = sm.Misc();
   uint32_t* K = sm.Kpl() + tid * (E / 4);
   const uint16_t* hq = sm.HardQ();
@@ -949,7 +949,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
   if constexpr (COOP) {
     queue_push<NT, E>(sm, &mi->hq_kb_n, !have);
     if (have && !STATEFUL) store_k();
-    __syncthreads();  // queue complete
+    LACB_SYNC();  // queue complete
     const uint32_t nh = mi->hq_kb_n;
     const bool pairs = nh <= (uint32_t)NT / 8u;
     if (pairs) {
@@ -963,14 +963,14 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
     if (STATK && warp == NW - 1u) block_static_k<NT, E>(sm, n);
     if (!STATEFUL) {
       LACB_PH(8);
-      __syncthreads();
+      LACB_SYNC();
       LACB_PH(9);
       if (tid == 0u) mi->hq_kb_n = 0u;  // consumed; the next pushes are at least one barrier away
       return;
     }
     if (have) sm.Flg()[tid] = flg;
     if (tid == 0u) mi->hq_n = 0u;
-    __syncthreads();  // flag words (and the k bytes of the queued chunks) complete
+    LACB_SYNC();  // flag words (and the k bytes of the queued chunks) complete
     if (tid == 0u) mi->hq_kb_n = 0u;
     if (!have) {  // pick up what the pairs produced for this chunk
 #pragma unroll
@@ -981,14 +981,14 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
     if (!STATEFUL) {
       store_k();
       LACB_PH(8);
-      __syncthreads();
+      LACB_SYNC();
       LACB_PH(9);
       return;
     }
     if (STATK && warp == NW - 1u) block_static_k<NT, E>(sm, n);
     sm.Flg()[tid] = flg;
     LACB_PH(6);
-    __syncthreads();
+    LACB_SYNC();
     LACB_PH(7);
   }
 
@@ -998,14 +998,14 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
   if constexpr (COOP) {
     queue_push<NT, E>(sm, &mi->hq_n, !done);
     LACB_PH(8);
-    __syncthreads();
+    LACB_SYNC();
     LACB_PH(9);
     const uint32_t nh = mi->hq_n;
     for (uint32_t i = warp * 2u; i < nh; i += NW * 2u)
       k_bias_pair<NT, E>(sm, hq[i], i + 1u < nh ? hq[i + 1u] : 0xFFFFu);
   }
   LACB_PH(8);
-  __syncthreads();
+  LACB_SYNC();
   LACB_PH(9);
 }
 
@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void k_series(const ASmem<NT, E>& sm, const Prep<NT, 
 // clipped to the block end.
 template <int NT, int E>
 __device__ __forceinline__ uint32_t zero_lookahead(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   uint32_t zm = pr.zmask;
   if (tid + 1u < (uint32_t)NT) {
     const uint4 v = reinterpret_cast<const uint4*>(sm.U())[swz_chunk((tid + 1u) * (E / 4))];
@@ -1058,7 +1058,7 @@ __device__ __forceinline__ Token token_rice_unsigned(uint32_t u, uint32_t k, uin
 template <int NT, int E, bool FAST, bool ZR, typename F>
 __device__ __forceinline__ void walk_thread(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                             const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   uint32_t u[E];
   load_u<NT, E>(sm, u);
   uint32_t kpk[E / 4];
@@ -1105,7 +1105,7 @@ __device__ __forceinline__ void walk_thread(const ASmem<NT, E>& sm, const Prep<N
 template <int NT, int E, typename F>
 __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                            const SegGeom& sg, uint32_t kinitA, uint32_t kinitB, F&& f) {
-  if (threadIdx.x * E >= n) return;
+  if (LACB_TID * E >= n) return;
   if (pr.any4) {
     if (sg.fast) walk_thread<NT, E, true, true>(sm, pr, n, sg, kinitA, kinitB, f);
     else walk_thread<NT, E, false, true>(sm, pr, n, sg, kinitA, kinitB, f);
@@ -1121,7 +1121,7 @@ __device__ __forceinline__ void walk_items(const ASmem<NT, E>& sm, const Prep<NT
 template <int NT, int E, bool STATEFUL>
 __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t p,
                                               uint32_t kinit_stateful) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   AMisc* mi = sm.Misc();
   const SegGeom sg = seg_geom<E>(g0, n, STATEFUL ? 0u : p);
   if (tid == 0) {
@@ -1237,7 +1237,7 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
       split_sum_add(&mi->tot_bin, b);
     }
     LACB_PH(10);
-    const uint32_t any_run = (uint32_t)__syncthreads_or((int)runA);  // also publishes the totals
+    const uint32_t any_run = (uint32_t)LACB_SYNC_OR((int)runA);  // also publishes the totals
     LACB_PH(11);
     return any_run;
   } else if (direct) {
@@ -1267,7 +1267,7 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
       if (run) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
     }
     LACB_PH(14);
-    __syncthreads();
+    LACB_SYNC();
     LACB_PH(15);
     return 1u;  // Fb holds sums, not prefixes
   } else {
@@ -1292,7 +1292,7 @@ __device__ __forceinline__ uint32_t cost_pass(const ASmem<NT, E>& sm, const Prep
     if (runA) atomicOr(&mi->hasrun_bits[sg.s0 >> 5], 1u << (sg.s0 & 31u));
     if (runB) atomicOr(&mi->hasrun_bits[(sg.s0 + 1u) >> 5], 1u << ((sg.s0 + 1u) & 31u));
     LACB_PH(14);
-    __syncthreads();
+    LACB_SYNC();
     LACB_PH(15);
     return 0u;
   }
@@ -1333,7 +1333,7 @@ __device__ __forceinline__ void walk_regs(const uint32_t (&u)[E], const uint32_t
 template <int NT, int E>
 __device__ __forceinline__ void k_chunk_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, const uint32_t (&u)[E],
                                                   uint32_t a0, u64 Pa, uint32_t (&kpk)[E / 4]) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   const u64 S = sm.Pthr()[tid + 1u] - pr.Pex;
   const uint32_t c_first = g0 - a0 + 1u, c_last = c_first + (uint32_t)E - 1u;
   const u64 rel = pr.Pex - Pa;
@@ -1377,7 +1377,7 @@ __device__ __forceinline__ void k_chunk_stateless(const ASmem<NT, E>& sm, const 
 template <int NT, int E>
 __device__ __forceinline__ void chunk_k_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, const uint32_t (&u)[E],
                                                   uint32_t sid, uint32_t a0, uint32_t (&kpk)[E / 4], uint32_t& kprev) {
-  const uint32_t g0 = threadIdx.x * E;
+  const uint32_t g0 = LACB_TID * E;
   const u64 Pa = sm.SegP()[sid];
   k_chunk_stateless<NT, E>(sm, pr, u, a0, Pa, kpk);
   if (g0 == a0) {
@@ -1394,7 +1394,7 @@ __device__ __forceinline__ void chunk_k_stateless(const ASmem<NT, E>& sm, const 
 template <int NT, int E, bool KINIT_FROM_MK, typename F>
 __device__ __forceinline__ void chunk_walk_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n,
                                                      uint32_t p, F&& f) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   const uint32_t base = n >> p, cnt = 1u << p, per_seg = (uint32_t)NT >> p;
   const uint32_t s0 = tid / per_seg, a0 = s0 * base, sid = cnt - 1u + s0;
   const bool last = (s0 + 1u < cnt) && (g0 + (uint32_t)E == a0 + base);
@@ -1432,7 +1432,7 @@ template <int NT, int E>
 __device__ __forceinline__ void chunk_costs_stateless(const ASmem<NT, E>& sm, const Prep<NT, E>& pr,
                                                       const uint32_t (&u)[E], uint32_t zm_all, uint32_t sid, uint32_t a0,
                                                       bool last, u64& rice, u64& zr, u64& bin, uint32_t& run) {
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   uint32_t kpk[E / 4], kprev;
   chunk_k_stateless<NT, E>(sm, pr, u, sid, a0, kpk, kprev);
   run = 0u;
@@ -1510,12 +1510,12 @@ __device__ __forceinline__ void chunk_costs_stateless(const ASmem<NT, E>& sm, co
 template <int NT, int E>
 __device__ __forceinline__ void levels_fused(const ASmem<NT, E>& sm, const Prep<NT, E>& pr, uint32_t n, uint32_t max_p) {
   constexpr uint32_t STR = ASmem<NT, E>::MAXSEG + 1u;
-  const uint32_t tid = threadIdx.x, g0 = tid * E;
+  const uint32_t tid = LACB_TID, g0 = tid * E;
   AMisc* mi = sm.Misc();
   u64* Fa = sm.FbAll();
   for (uint32_t i = tid; i < 3u * STR; i += NT) Fa[i] = 0ull;
   if (tid < 16u) mi->hasrun_all[tid] = 0u;
-  __syncthreads();
+  LACB_SYNC();
   uint32_t u[E];
   load_u<NT, E>(sm, u);
   const uint32_t zm_all = pr.any4 ? zero_lookahead(sm, pr, n) : 0u;
@@ -1561,7 +1561,7 @@ __device__ __forceinline__ void levels_fused(const ASmem<NT, E>& sm, const Prep<
       if (rn) atomicOr(&mi->hasrun_all[sid >> 5], 1u << (sid & 31u));
     }
   }
-  __syncthreads();
+  LACB_SYNC();
 }
 
 // Exact emitted bit count of the thread's samples for the final decision.
