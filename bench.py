@@ -31,6 +31,12 @@ from pathlib import Path
 
 import numpy as np
 
+# The host pipelines of the library keep up to twelve slice streams in flight; the CUDA runtime maps streams onto 8
+# hardware queues by default and slices that share a queue serialise.  Must be set before CUDA starts (`lac_cli serve`
+# does the same); the library only goes beyond four decode slices in flight when it sees this setting.  It lengthens
+# CUDA's start-up by 1 - 2.5 s (tools/cli_conn_check.py), which is why one-shot CLI runs leave it alone.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))

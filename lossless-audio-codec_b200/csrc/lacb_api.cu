@@ -50,6 +50,23 @@ struct lacb_ctx {
   uint32_t last_enc_blocks = 0, last_enc_channels = 0;
   uint64_t last_enc_frames = 0;
   uint32_t max_streams = 0;         // lacb_set_concurrency: 0 = automatic, n = at most n slices in flight
+  // Slice contexts of the host pipelines launch the analysis / emit kernels with one CTA per job instead of one
+  // persistent CTA per SM.  A persistent grid of slice i + 1 takes every SM the moment the grid of slice i drains, and
+  // holds all of them to its end: the one-CTA kernels of slice i that follow its analysis (block sizes -> offsets, which
+  // the host waits for before it can queue the emit kernel, the payload copy and the NEXT slice's input copy) then sat
+  // behind the whole analysis of slice i + 1 (LACB_TRACE: "sizes known" arrived in pairs, ~2 ms of idle SMs per large
+  // slice).  With short-lived CTAs an SM frees up every few microseconds and the older grid's kernels get it.
+  bool per_job_grid = false;
+  // ... and run them on a second stream of lower priority than everything else of the slice (copies, de-interleave,
+  // stereo decision, job lists, autocorrelation, Levinson, block offsets): whenever an SM frees up, the small kernels of
+  // this and of the NEXT slice go first, so they finish under the running analysis instead of queueing behind it with
+  // their launch and dependency latencies exposed (6 slices x ~0.3 ms), and a slice's sizes reach the host the moment
+  // its analysis ends.
+  // The emit kernel sits in between: grids of one priority are served in launch order, and the analyses of the next
+  // slices were launched before this slice's sizes were known -- at their priority every emit kernel would run after
+  // the LAST analysis and the payload copies would pile up behind the pipeline instead of hiding under it.
+  cudaStream_t stream_heavy = nullptr, stream_mid = nullptr;
+  cudaEvent_t ev_x = nullptr;
 };
 
 namespace {
@@ -193,7 +210,7 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
   {
     auto kb = k_build_jobs<false>;
     LACB_LAUNCH(kb, 1, 1024, 0, st, cfg, as<uint32_t>(ctx->flags), as<uint32_t>(ctx->jobs), counts);
-    const uint32_t fgrid = lacb_umin(nb * 4u, (uint32_t)ctx->sms);
+    const uint32_t fgrid = ctx->per_job_grid ? nb * 4u : lacb_umin(nb * 4u, (uint32_t)ctx->sms);
     auto ka = k_autocorr_stream<256>;
     LACB_LAUNCH(ka, lacb_umin(nb * 4u, (uint32_t)ctx->sms * 2u), 256, 0, st, src, as<uint32_t>(ctx->jobs), counts,
                 as<i64>(ctx->acor));
@@ -201,9 +218,15 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
     LACB_LAUNCH(kl, lacb_umin((nb * 4u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs),
                 counts, as<i64>(ctx->acor), as<LpcQ>(ctx->lpcq));
     CK(cudaEventRecord(ctx->ev[EV_LPC], st));
+    cudaStream_t sh = ctx->stream_heavy ? ctx->stream_heavy : st;
+    if (sh != st) CK(cudaStreamWaitEvent(sh, ctx->ev[EV_LPC], 0));
     auto kz = k_analyze<FULL_NT, FULL_E, false>;
-    LACB_LAUNCH(kz, fgrid, FULL_NT, kFullSmem, st, src, cfg, as<uint32_t>(ctx->jobs), counts,
+    LACB_LAUNCH(kz, fgrid, FULL_NT, kFullSmem, sh, src, cfg, as<uint32_t>(ctx->jobs), counts,
                 as<LpcQ>(ctx->lpcq), as<ChanRec>(ctx->recs), (uint32_t*)nullptr);
+    if (sh != st) {
+      CK(cudaEventRecord(ctx->ev_x, sh));
+      CK(cudaStreamWaitEvent(st, ctx->ev_x, 0));
+    }
   }
   CK(cudaEventRecord(ctx->ev[EV_ANALYZE], st));
 
@@ -254,9 +277,16 @@ int encode_emit(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL, co
   *total = tot;
   CKR(ensure(ctx, ctx->payload, (size_t)tot + 64));
   {
+    // (everything queued on st so far has completed: the host has just read this slice's sizes)
+    cudaStream_t sh = ctx->stream_mid ? ctx->stream_mid : st;
     auto ke = k_emit<FULL_NT, FULL_E>;
-    LACB_LAUNCH(ke, lacb_umin(nb * cfg.channels, (uint32_t)ctx->sms), FULL_NT, kFullSmem, st, src, cfg,
+    LACB_LAUNCH(ke, ctx->per_job_grid ? nb * cfg.channels : lacb_umin(nb * cfg.channels, (uint32_t)ctx->sms), FULL_NT,
+                kFullSmem, sh, src, cfg,
                 as<uint32_t>(ctx->flags), as<ChanRec>(ctx->recs), as<u64>(ctx->blk_off), as<uint8_t>(ctx->payload));
+    if (sh != st) {
+      CK(cudaEventRecord(ctx->ev_x, sh));
+      CK(cudaStreamWaitEvent(st, ctx->ev_x, 0));
+    }
   }
   CK(cudaEventRecord(ctx->ev[EV_EMIT], st));
   return 0;
@@ -367,6 +397,9 @@ void lacb_destroy(lacb_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int i = 0; i < EV_COUNT; ++i)
     if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream_heavy) cudaStreamDestroy(ctx->stream_heavy);
+  if (ctx->stream_mid) cudaStreamDestroy(ctx->stream_mid);
+  if (ctx->ev_x) cudaEventDestroy(ctx->ev_x);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -510,9 +543,14 @@ static uint32_t slice_blocks(const lacb_ctx* ctx, uint32_t channels) {
   return per_wave * 14u;
 }
 // slice contexts the host-buffer decode keeps in flight
+// Four by default: the CUDA runtime maps streams onto 8 hardware queues unless CUDA_DEVICE_MAX_CONNECTIONS says
+// otherwise, and slices whose streams share a queue serialise (6 - 16 slices in flight: 13 - 19 ms instead of 11.3 ms
+// for 600 s of 24/96).  A process that raised the queue count before CUDA started (`lac_cli serve` and bench.py set 32) gets
+// twelve: the first slice is a twelfth of the input, so the device-to-host copies start earlier (10.5 ms).
 static uint32_t dec_kids() {
   static const long forced = getenv("LACB_DEC_KIDS") ? atol(getenv("LACB_DEC_KIDS")) : 0;  // tuning
-  return forced >= 2 && forced <= 16 ? (uint32_t)forced : 4u;
+  static const long conns = getenv("CUDA_DEVICE_MAX_CONNECTIONS") ? atol(getenv("CUDA_DEVICE_MAX_CONNECTIONS")) : 8;
+  return forced >= 2 && forced <= 16 ? (uint32_t)forced : (conns >= 16 ? 12u : 4u);
 }
 static double trace_now() {
   struct timespec ts;
@@ -539,6 +577,28 @@ static int ensure_kids(lacb_ctx* ctx, size_t count = 2) {
       ctx->err = "cannot create slice context";
       return rc;
     }
+    static const bool persistent = getenv("LACB_SLICE_PERSISTENT") != nullptr;  // A/B knobs
+    static const bool one_prio = getenv("LACB_SLICE_ONE_PRIORITY") != nullptr;
+    k->per_job_grid = !persistent;
+    if (!persistent && !one_prio) {
+      // the slice's own stream becomes a high-priority one, the heavy kernels get a stream of the lowest priority
+      int least = 0, greatest = 0;
+      cudaDeviceGetStreamPriorityRange(&least, &greatest);
+      cudaStream_t hi = nullptr;
+      if (greatest != least && cudaStreamCreateWithPriority(&hi, cudaStreamNonBlocking, greatest) == cudaSuccess &&
+          cudaStreamCreateWithPriority(&k->stream_heavy, cudaStreamNonBlocking, least) == cudaSuccess &&
+          cudaStreamCreateWithPriority(&k->stream_mid, cudaStreamNonBlocking, (least + greatest) / 2) == cudaSuccess &&
+          cudaEventCreateWithFlags(&k->ev_x, cudaEventDisableTiming) == cudaSuccess) {
+        cudaStreamDestroy(k->stream);
+        k->stream = hi;
+      } else {
+        if (hi) cudaStreamDestroy(hi);
+        if (k->stream_heavy) cudaStreamDestroy(k->stream_heavy);
+        if (k->stream_mid) cudaStreamDestroy(k->stream_mid);
+        k->stream_heavy = k->stream_mid = nullptr;
+        cudaGetLastError();
+      }
+    }
     ctx->kids.push_back(k);
   }
   return 0;
@@ -560,16 +620,19 @@ static int enc_slice_begin(lacb_ctx* ctx, const lacb_enc_params* prm, int layout
   CKR(ensure(ctx, ctx->planeL, fr * 4));
   if (prm->channels == 2) CKR(ensure(ctx, ctx->planeR, fr * 4));
   bool validate = prm->validate_range != 0;
+  CK(cudaEventRecord(ctx->ev[EV_START], st));
   if (layout == LACB_PLANAR_I32) {
     CK(cudaMemcpyAsync(ctx->planeL.p, static_cast<const int32_t*>(pcm_a) + f0, fr * 4, cudaMemcpyHostToDevice, st));
     if (prm->channels == 2)
       CK(cudaMemcpyAsync(ctx->planeR.p, static_cast<const int32_t*>(pcm_b) + f0, fr * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], st));
   } else {
     const uint32_t bps = prm->bit_depth / 8;
     const size_t fb = (size_t)prm->channels * bps;
     CKR(ensure(ctx, ctx->packed_in, fr * fb + 4));
     CK(cudaMemcpyAsync(ctx->packed_in.p, static_cast<const uint8_t*>(pcm_a) + f0 * fb, fr * fb, cudaMemcpyHostToDevice,
                        st));
+    CK(cudaEventRecord(ctx->ev[EV_H2D], st));
     const uint32_t grid = lacb_umin((uint32_t)((fr + 255) / 256), (uint32_t)ctx->sms * 16u);
     auto kd = k_deinterleave;
     LACB_LAUNCH(kd, grid ? grid : 1u, 256, 0, st, as<uint8_t>(ctx->packed_in), (u64)fr, prm->channels, bps,
@@ -586,18 +649,39 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
   // slice's emit kernel, which cannot start before the analysis of slice i (all SMs, all registers) has finished: the
   // copy therefore ran AFTER the analysis it was meant to hide under, ~2 ms of idle SMs per large slice.  The third
   // context's stream is free when slice i + 1 is queued (its last emit only waited for the analysis of slice i - 1).
-  constexpr uint32_t NK = 3u;
+  // Round 2, later: FOUR contexts, and the input of slice i + 2 is queued before the host waits for the sizes of slice
+  // i -- with a look-ahead of one slice the copy of slice i + 1 only started when the sizes of slice i - 1 were known,
+  // i.e. when its own analysis could already have begun (1.1 ms of idle SMs in front of the third slice).
+  static const uint32_t NK = getenv("LACB_ENC_KIDS") ? (uint32_t)atoi(getenv("LACB_ENC_KIDS")) : 4u;  // tuning knob
+  static const uint32_t AHEAD = getenv("LACB_ENC_AHEAD") ? (uint32_t)atoi(getenv("LACB_ENC_AHEAD")) : 2u;
   const uint32_t nkenc = ctx->max_streams >= 2u ? lacb_umin(NK, ctx->max_streams) : NK;  // the caller's cap on slices in flight
+  const uint32_t ahead = lacb_umin(AHEAD ? AHEAD : 1u, nkenc - 1u);  // slices queued beyond the one being collected
   CKR(ensure_kids(ctx, nkenc));
   const uint32_t nb = (uint32_t)((frames + kMaxBlock - 1) / kMaxBlock);
   // Slice plan: the first slices are short (2, 4, 8 waves of jobs) so that the kernels start after a
   // fraction of a millisecond of copying and every later copy hides under the slice before it.
   const uint32_t sb = slice_blocks(ctx, prm->channels);
+  // The plan ends the way it starts: what follows the last analysis -- that slice's emit kernel and payload copy --
+  // is exposed, so the last two slices are 4 and 2 waves.
   std::vector<uint32_t> cut{0u};  // cut[i] = first block of slice i, cut[ns] = nb
-  if (getenv("LACB_SLICE_BLOCKS") == nullptr)
-    for (uint32_t w = 2u; w < 14u && cut.back() + sb / 14u * w + sb < nb; w *= 2u) cut.push_back(cut.back() + sb / 14u * w);
-  while (cut.back() + sb < nb) cut.push_back(cut.back() + sb);
-  cut.push_back(nb);
+  const uint32_t wave = sb / 14u;
+  uint32_t main_end = nb;  // blocks in front of the short closing slices
+  if (getenv("LACB_SLICE_BLOCKS") == nullptr) {
+    for (uint32_t w = 2u; w < 14u && cut.back() + wave * w + sb < nb; w *= 2u) cut.push_back(cut.back() + wave * w);
+    if (cut.back() + sb + 6u * wave < nb) main_end = nb - 6u * wave;
+  }
+  {
+    // the middle in equal slices of at most sb blocks (whole waves)
+    const uint32_t mid = main_end - cut.back();
+    const uint32_t nmid = (mid + sb - 1u) / sb;
+    const uint32_t each = nmid ? ((mid + nmid - 1u) / nmid + wave - 1u) / (wave ? wave : 1u) * (wave ? wave : 1u) : 0u;
+    while (each && cut.back() + each < main_end) cut.push_back(cut.back() + each);
+    if (main_end > cut.back()) cut.push_back(main_end);
+  }
+  if (main_end < nb) {
+    cut.push_back(main_end + 4u * wave);
+    cut.push_back(nb);
+  }
   const uint32_t ns = (uint32_t)cut.size() - 1u;
   uint8_t* host = dst;
   uint64_t cap = dst_cap;
@@ -618,10 +702,22 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
     return rc;
   };
   uint64_t f0, fr;
-  slice_range(0, &f0, &fr);
+  if (trace_on()) cudaEventRecord(ctx->ev[EV_START], ctx->stream);
+  uint32_t begun = 0;  // slices whose input copy and analysis are queued
+  auto begin_upto = [&](uint32_t want) -> int {  // queue slices [begun, want)
+    for (; begun < want && begun < ns; ++begun) {
+      uint64_t g0, gr;
+      slice_range(begun, &g0, &gr);
+      lacb_ctx* kn = ctx->kids[begun % nkenc];
+      const int rc = enc_slice_begin(kn, prm, layout, pcm_a, pcm_b, g0, gr);
+      if (rc != 0) { ctx->err = kn->err; return rc; }
+      TRACE("enc slice %u queued", begun);
+    }
+    return 0;
+  };
   {
-    const int rc = enc_slice_begin(ctx->kids[0], prm, layout, pcm_a, pcm_b, f0, fr);
-    if (rc != 0) { ctx->err = ctx->kids[0]->err; return fail(rc); }
+    const int rc = begin_upto(ahead);
+    if (rc != 0) return fail(rc);
   }
   uint64_t off = 0;
   bool overflow = false;
@@ -635,13 +731,9 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
   }
   for (uint32_t i = 0; i < ns; ++i) {
     lacb_ctx* k = ctx->kids[i % nkenc];
-    if (i + 1u < ns) {  // next slice: its copies run under the analysis of slice i, its analysis queues up behind it
-      uint64_t g0, gr;
-      slice_range(i + 1u, &g0, &gr);
-      lacb_ctx* kn = ctx->kids[(i + 1u) % nkenc];
-      const int rc = enc_slice_begin(kn, prm, layout, pcm_a, pcm_b, g0, gr);
-      if (rc != 0) { ctx->err = kn->err; return fail(rc); }
-      TRACE("enc slice %u queued", i + 1u);
+    {  // the next slices: their copies run under the analysis of slice i, their analyses queue up behind it
+      const int rc = begin_upto(i + 1u + ahead);
+      if (rc != 0) return fail(rc);
     }
     slice_range(i, &f0, &fr);
     uint64_t total = 0;
@@ -664,6 +756,7 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
       CKK(k, [&]() -> int {
         lacb_ctx* ctx = k;  // CK reports into the slice context
         CK(cudaMemcpyAsync(host + off, ctx->payload.p, total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[EV_D2H], ctx->stream));
         return 0;
       }());
     if (bb_stage)
@@ -682,6 +775,16 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
     }
   }
   TRACE("enc drained");
+  if (trace_on()) {  // device timeline of the last slices (a slice context keeps the events of its last slice only)
+    for (uint32_t i = ns > nkenc ? ns - nkenc : 0u; i < ns; ++i) {
+      lacb_ctx* k = ctx->kids[i % nkenc];
+      float t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      const int evs[9] = {EV_START, EV_H2D, EV_PREP, EV_STEREO, EV_LPC, EV_ANALYZE, EV_FINAL, EV_EMIT, EV_D2H};
+      for (int e = 0; e < 9; ++e) cudaEventElapsedTime(&t[e], ctx->ev[EV_START], k->ev[evs[e]]);
+      TRACE("enc slice %u: start %.2f h2d %.2f prep %.2f stereo %.2f lpc %.2f analyze %.2f sizes %.2f emit %.2f d2h %.2f ms", i,
+            t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8]);
+    }
+  }
   memset(&ctx->timing, 0, sizeof ctx->timing);  // stage times are per slice context, not aggregated
   if (block_bytes) memcpy(block_bytes, bb_stage, (size_t)nb * 4);
   *payload_bytes = off;

@@ -1063,7 +1063,11 @@ __global__ void __launch_bounds__(NT) k_emit(PcmSrc src, EncCfg cfg, const uint3
     const u64 abs0 = out_off * 8ull;           // absolute bit address of the first bit
     const u64 absEnd = abs0 + total_bytes * 8ull;
     for (u64 wstart = abs0 & ~31ull; wstart < absEnd; wstart += (u64)W * 32ull) {
-      for (uint32_t i = tid; i < W; i += NT) stg[i] = 0u;
+      // only the words this window will hand to the copy-out below (a 16384-sample block of 24-bit audio fills
+      // less than half of the 64 KB plane)
+      const u64 wleft = (absEnd - wstart + 31ull) >> 5;
+      const uint32_t wuse = wleft < (u64)W ? (uint32_t)wleft : W;
+      for (uint32_t i = tid; i < wuse; i += NT) stg[i] = 0u;
       __syncthreads();
       const i64 rel0 = (i64)(abs0 - wstart);  // staging position of bit 0 of the channel-block (may be negative)
       // header

@@ -491,6 +491,11 @@ static int run_command(int argc, char** argv) {
 }
 
 int main(int argc, char** argv) {
+  // A resident server asks for more hardware queues than the default 8, so that the slice streams of the host pipelines
+  // do not share one (read by the CUDA runtime when it starts; the library keeps twelve instead of four decode slices
+  // in flight when it sees it).  Not for one-shot runs: the extra queues add 1 - 2.5 s to CUDA's start-up
+  // (tools/cli_conn_check.py), far more than the 0.7 ms per decode they save.
+  if (argc >= 2 && std::string(argv[1]) == "serve") setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   // A one-shot encode / decode on one GPU only needs that GPU: hiding the others from the CUDA runtime keeps
   // its initialisation from enumerating and mapping every device of an 8-GPU box (honours an existing setting).
   if (argc >= 2 && (std::string(argv[1]) == "encode" || std::string(argv[1]) == "decode")) {
