@@ -188,11 +188,15 @@ int encode_analysis(lacb_ctx* ctx, const lacb_enc_params* prm, const int32_t* dL
     LACB_LAUNCH(kl, lacb_umin((nb * 12u + 63u) / 64u, (uint32_t)ctx->sms * 4u), 64, 0, st, src, as<uint32_t>(ctx->jobs_p),
                 counts + 1, as<i64>(ctx->acor_p), as<LpcQ>(ctx->lpcq_p));
     // probe warps run in gangs of kProbeGang per CTA (see k_analyze)
-    static const uint32_t gang = [] {  // experiment knob, 1..32 sub-blocks per CTA
+    static const uint32_t forced_gang = [] {  // experiment knob, 1..32 sub-blocks per CTA
       const char* e = getenv("LACB_PROBE_GANG");
       const int v = e ? atoi(e) : 0;
-      return (uint32_t)(v >= 1 && v <= 32 ? v : (int)kProbeGang);
+      return (uint32_t)(v >= 1 && v <= 32 ? v : 0);
     }();
+    // full gangs when every SM gets 32 probes or more; a short input spreads its probes over all SMs in smaller gangs
+    uint32_t gang = kProbeGang;
+    while (gang > 4u && nb * 12u <= (uint32_t)ctx->sms * (gang / 2u)) gang /= 2u;
+    if (forced_gang) gang = forced_gang;
     const uint32_t ggrid = lacb_umin((nb * 12u + gang - 1u) / gang, (uint32_t)ctx->sms * (32u / gang));
     auto kz = k_analyze<PROBE_NT, PROBE_E, true>;
     LACB_LAUNCH(kz, ggrid, PROBE_NT * gang, kProbeSmem * gang, st, src, cfg, as<uint32_t>(ctx->jobs_p),
