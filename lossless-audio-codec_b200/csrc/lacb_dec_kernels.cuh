@@ -905,6 +905,30 @@ __device__ __forceinline__ void cp_async_wait() {
 #endif
 }
 
+// exact double arithmetic on integers below 2^53 (the LPC restore chain)
+__device__ __forceinline__ double fma_exact(double a, double b, double c) {
+#ifdef LACB_EMU
+  return a * b + c;  // |a * b| < 2^53: the product is exact, so no fused operation is needed for exactness
+#else
+  return __fma_rn(a, b, c);
+#endif
+}
+__device__ __forceinline__ double floor_exact(double x) {
+#if defined(LACB_EMU) || defined(LACB_FLOOR_FRND)
+  return floor(x);  // (on the device: FRND.F64.FLOOR, measured 0.69 ms per restore against 0.62 ms for the two adds)
+#else
+  // |x| < 2^51: x + (2^52 + 2^51) rounded towards minus infinity is floor(x) + (2^52 + 2^51) -- two adds on the FP64 pipe
+  return __dadd_rn(__dadd_rd(x, 6755399441055744.0), -6755399441055744.0);
+#endif
+}
+__device__ __forceinline__ int32_t d2i_sat(double v) {  // integer-valued v; saturates like cvt.rni.s32.f64
+#ifdef LACB_EMU
+  return v >= 2147483647.0 ? 2147483647 : (v <= -2147483648.0 ? (int32_t)(-2147483647 - 1) : (int32_t)v);
+#else
+  return __double2int_rn(v);
+#endif
+}
+
 constexpr int kRestoreDepth = 6;  // chunks of 8 samples in flight per thread
 
 // Runs the recurrence over x[0..n) in order, 8 samples at a time.  One thread owns the whole
@@ -1053,27 +1077,37 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
     // Measured: the kernel time does not move with the shape of the chain or the prefetch depth but drops
     // from 0.98 to 0.43 ms without the arithmetic -- with one warp per scheduler the twelve 32x32->64
     // multiply-adds per sample are paid at their issue cost whatever the number of active lanes.
-    int32_t cf[13];
+    // Round 2, last session: the twelve multiply-adds run on the FP64 pipe.  A 32x32->64 integer multiply-add
+    // (IMAD.WIDE) issues every ~5.5 cycles from the single warp a scheduler has here (measured: 66 cycles per sample
+    // for twelve), a DFMA every 2; and every quantity of the chain is an integer below 2^53 in magnitude, so doubles
+    // hold it EXACTLY: |c_t * s| <= 2^15 * 2^31, a sum of twelve < 2^50, its floor(/ 2^15) and the sample < 2^36.  The
+    // prediction is floor(sum * 2^-15) (exact scaling, exact floor), the sample stays a double along the chain (the
+    // conversions of the residual coming in and of the sample going out are off the chain), and the int32 range
+    // verdict is a comparison of the exact double.
+    // The coefficients carry the 2^-15 (an exact scaling: the sums become multiples of 2^-15 below 2^35), and the
+    // residual -- an integer -- is added to the accumulator before the last term arrives, so the sample is
+    // floor(A[1] + c_1 * s): the chain from sample to sample is one DFMA and one floor.
+    double cf[13];
 #pragma unroll
-    for (int t = 1; t <= 12; ++t) cf[t] = (uint32_t)t <= order ? (int32_t)c[t] : 0;
-    i64 A[14];
+    for (int t = 1; t <= 12; ++t) cf[t] = (uint32_t)t <= order ? (double)c[t] * 0.000030517578125 : 0.0;
+    double A[14];
 #pragma unroll
-    for (int t = 0; t < 14; ++t) A[t] = 0;
-    int32_t h1 = 0;  // the previous sample
+    for (int t = 0; t < 14; ++t) A[t] = 0.0;
+    double h1 = 0.0;  // the previous sample
     return restore_chunked(
         x, n, stage, stride,
         [&](uint32_t, int32_t& val, i64& aux) {
+          const double pre = A[1] + (double)val;  // everything but the newest sample's term (off the chain)
 #pragma unroll
-          for (int t = 1; t <= 12; ++t) A[t] = mad_wide(cf[t], h1, A[t]);
-          aux = A[1] >> 15;  // the prediction, kept in 64 bits for the verdict
-          val = (int32_t)((uint32_t)val + (uint32_t)aux);
-          h1 = val;
+          for (int t = 2; t <= 12; ++t) A[t] = fma_exact(cf[t], h1, A[t]);
+          const double vd = floor_exact(fma_exact(cf[1], h1, pre));
+          aux = (vd < -2147483648.0 || vd > 2147483647.0) ? 1 : 0;  // the reference's int32 range verdict
+          val = d2i_sat(vd);
+          h1 = vd;
 #pragma unroll
           for (int t = 1; t <= 12; ++t) A[t] = A[t + 1];  // A[13] stays 0
         },
-        [](uint32_t, int32_t in, int32_t out, i64 aux, int32_t, int32_t, int32_t, int32_t) {
-          return aux + (i64)in == (i64)out;
-        });
+        [](uint32_t, int32_t, int32_t, i64 aux, int32_t, int32_t, int32_t, int32_t) { return aux == 0; });
   }
   for (uint32_t i = 0; i < n; ++i) {  // orders 13..32: legal in the format, never produced by the encoder
     i64 acc = 0;

@@ -13,6 +13,7 @@ from __future__ import annotations
 import argparse
 import ctypes as C
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -89,7 +90,7 @@ def main():
     q = 10 if args.quick else 1
     global ONLY
     ONLY = args.only
-    cd = load_package().Codec(0)
+    cd = load_package().Codec(0, os.environ.get("LACB_LIB"))  # LACB_LIB: an experimental build of the library
     lines = []
     t0 = time.time()
     lines.append(run_case(cd, "C1 60 s 16/44.1 stereo auto", 1, 60, 44100, 16, 2, 2))
