@@ -337,7 +337,7 @@ __global__ void k_decode_one(const uint8_t* data, u64 size, u64 padded, u64 bit_
   __syncwarp();
   if (lane != 0u) return;
   const bool ran_out = !ok && rd_over(r);
-  if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef, stage1, 1u);
+  if (ok) ok = restore_block(out, n, hdr.type, hdr.order, hdr.coef, stage1, 1u, true);
   result[0] = ok ? 1ull : 0ull;
   result[1] = ok ? rd_pos(r) - r.start - bit_off : 0ull;
   result[2] = ran_out ? 1ull : 0ull;
@@ -376,6 +376,20 @@ int lacb_create(int device, lacb_ctx** out) {
                        (int)ASmem<FULL_NT, FULL_E>::BYTES);
   cudaFuncSetAttribute(k_analyze<PROBE_NT, PROBE_E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)(kProbeSmem * 32));
+  // The decoder's kernels of different slices share SMs in the host pipeline (a restore CTA next to the parser warps
+  // of later slices).  An SM's shared-memory carve-out is chosen from the preference of the kernel that first lands on
+  // it and can only change when the SM is empty: with the default preference the parsers (2 KB each) left the SMs
+  // configured too small for a restore CTA's 12 KB of staging, and the restore kernels of the early slices waited
+  // until the parsers of ALL slices had retired (LACB_TRACE: restore of slice 0 done at 8.2 instead of 3.7 ms, decode
+  // 13.7 instead of 10.4 ms) -- or not, depending on the build, because the driver's choice follows the kernels'
+  // resource use.  All of them ask for the largest carve-out.
+  cudaFuncSetAttribute(k_parse_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_parse_serial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_restore_order, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_restore_blocks, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_merge_restore_errors, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(k_finish_pcm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(k_emit<FULL_NT, FULL_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)ASmem<FULL_NT, FULL_E>::BYTES);
   if (cudaGetLastError() != cudaSuccess) {
@@ -1033,7 +1047,8 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   CK(cudaMemcpyAsync(ctx->d_size.p, h_size, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->d_bytes.p, h_bytes, (size_t)n_blocks * 4, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev[EV_H2D], st));
-  DecCfg cfg{prm->channels, prm->stereo_mode, prm->bit_depth, n_blocks};
+  static const int lpc_fp64 = getenv("LACB_RESTORE_FP64") ? atoi(getenv("LACB_RESTORE_FP64")) : 1;  // A/B knob: 0 = integer chain
+  DecCfg cfg{prm->channels, prm->stereo_mode, prm->bit_depth, n_blocks, (uint32_t)(lpc_fp64 != 0)};
   CKR(ensure(ctx, ctx->d_hdrs, (size_t)n_blocks * 2 * sizeof(ChanHdr)));
   if (serial) {
     CKR(ensure(ctx, ctx->misc, 64));
@@ -1052,9 +1067,13 @@ static int decode_common(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_
   CKR(ensure(ctx, ctx->d_order, ((size_t)n_blocks * 2 + 8 * 32 + 1) * 4));
   uint32_t* d_order = as<uint32_t>(ctx->d_order);
   auto ko = k_restore_order;
-  LACB_LAUNCH(ko, 1, 1024, 0, st, cfg, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err), d_order + 1, d_order);
+  // 256 threads, not 1024: in the host pipelines this one-CTA kernel starts while the parser warps of the other slices
+  // fill the SMs (24 warps of 64 registers: 16 K registers free per SM); a 1024-thread CTA (20 K registers) did not fit
+  // anywhere until parsers retired -- depending on how the parser CTAs had spread, a slice's restore waited up to 6 ms
+  LACB_LAUNCH(ko, 1, 256, 0, st, cfg, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err), d_order + 1, d_order);
+  CK(cudaEventRecord(ctx->ev[EV_STEREO], st));  // (decode: the restore order is known)
   auto kr = k_restore_blocks;
-  LACB_LAUNCH(kr, (n_blocks * prm->channels + 8u * 32u + 63u) / 64u, 64, 0, st, cfg, as<u64>(ctx->d_fs),
+  LACB_LAUNCH(kr, (n_blocks * prm->channels + 8u * 32u + kRestoreTpb - 1u) / kRestoreTpb, kRestoreTpb, 0, st, cfg, as<u64>(ctx->d_fs),
               as<uint32_t>(ctx->d_size), dL, dR, as<ChanHdr>(ctx->d_hdrs), as<uint32_t>(ctx->d_err), d_order + 1,
               d_order);
   auto km = k_merge_restore_errors;
@@ -1257,11 +1276,11 @@ int lacb_decode(lacb_ctx* ctx, const lacb_dec_params* prm, const uint8_t* payloa
       const uint32_t b0 = i * sb, b1 = b0 + sb < n_blocks ? b0 + sb : n_blocks;
       const int r = decode_check_errors(k, b1 - b0, err, false, b0);  // waits for slice i only
       if (trace_on() && r == 0) {  // device timeline of the slice, relative to the start of the call
-        float t[6] = {0, 0, 0, 0, 0, 0};
-        const int evs[6] = {EV_START, EV_H2D, EV_LPC, EV_ANALYZE, EV_EMIT, EV_D2H};
-        for (int e = 0; e < 6; ++e) cudaEventElapsedTime(&t[e], ctx->ev[EV_START], k->ev[evs[e]]);
-        TRACE("dec slice %u done: start %.2f h2d %.2f parse %.2f restore %.2f finish %.2f d2h %.2f ms", i, t[0], t[1],
-              t[2], t[3], t[4], t[5]);
+        float t[7] = {0, 0, 0, 0, 0, 0, 0};
+        const int evs[7] = {EV_START, EV_H2D, EV_LPC, EV_STEREO, EV_ANALYZE, EV_EMIT, EV_D2H};
+        for (int e = 0; e < 7; ++e) cudaEventElapsedTime(&t[e], ctx->ev[EV_START], k->ev[evs[e]]);
+        TRACE("dec slice %u done: start %.2f h2d %.2f parse %.2f order %.2f restore %.2f finish %.2f d2h %.2f ms", i, t[0],
+              t[1], t[2], t[3], t[4], t[5], t[6]);
       }
       if (r != 0) ctx->err = k->err;
       return r;

@@ -961,11 +961,14 @@ __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* st
       }
       cp_async_commit();  // one group per chunk, empty groups keep the count uniform
     }
-    for (uint32_t c0 = 0; c0 < nch; c0 += D) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const uint32_t c = c0 + (uint32_t)d;
-        if (c < nch) {
+    // One compact loop body (a chunk of 8 samples, the staging slot by a running index): with the body unrolled over
+    // the D slots the LPC loop was ~35 KB of code, and sharing an SM with the parser warps of other slices (host
+    // pipelines) it ran up to six times slower depending on where the build happened to place it (instruction fetch).
+    uint32_t d = 0u;
+#pragma unroll 1
+    for (uint32_t c = 0; c < nch; ++c) {
+      {
+        {
           cp_async_wait<D - 1>();  // the oldest group (chunk c) has landed
           const int4 lo = stage[(2 * d) * stride], hi = stage[(2 * d + 1) * stride];
           if (c + D < nch) {
@@ -994,6 +997,7 @@ __device__ __forceinline__ bool restore_chunked(int32_t* x, uint32_t n, int4* st
           x4[2 * c] = make_int4(v[4], v[5], v[6], v[7]);
           x4[2 * c + 1] = make_int4(v[8], v[9], v[10], v[11]);
           t4 = v[8]; t3 = v[9]; t2 = v[10]; t1 = v[11];
+          d = d + 1u == (uint32_t)D ? 0u : d + 1u;
         }
       }
     }
@@ -1041,7 +1045,7 @@ __device__ __forceinline__ bool restore_fixed(int32_t* x, uint32_t n, int4* stag
 
 // restore_*_in_place, block/decoder.cpp:308-403: every reconstructed sample must fit int32
 __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t type, uint32_t order, const int16_t* c,
-                                              int4* stage, uint32_t stride) {
+                                              int4* stage, uint32_t stride, bool lpc_fp64) {
   if (type == PRED_FIXED) {
     switch (order) {
       case 0: return true;
@@ -1062,6 +1066,30 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
         },
         [](uint32_t i, int32_t in, int32_t out, i64, int32_t g1, int32_t g2, int32_t, int32_t) {
           return i < 2u || (i64)in + ((3 * (i64)g1 - g2) >> 2) == (i64)out;
+        });
+  }
+  if (order <= 12u && !lpc_fp64) {
+    // The integer form of the chain below (LACB_RESTORE_FP64=0): the comparison path, 0.98 ms against 0.60 ms.
+    int32_t cf[13];
+#pragma unroll
+    for (int t = 1; t <= 12; ++t) cf[t] = (uint32_t)t <= order ? (int32_t)c[t] : 0;
+    i64 A[14];
+#pragma unroll
+    for (int t = 0; t < 14; ++t) A[t] = 0;
+    int32_t h1 = 0;  // the previous sample
+    return restore_chunked(
+        x, n, stage, stride,
+        [&](uint32_t, int32_t& val, i64& aux) {
+#pragma unroll
+          for (int t = 1; t <= 12; ++t) A[t] = mad_wide(cf[t], h1, A[t]);
+          aux = A[1] >> 15;  // the prediction, kept in 64 bits for the verdict
+          val = (int32_t)((uint32_t)val + (uint32_t)aux);
+          h1 = val;
+#pragma unroll
+          for (int t = 1; t <= 12; ++t) A[t] = A[t + 1];  // A[13] stays 0
+        },
+        [](uint32_t, int32_t in, int32_t out, i64 aux, int32_t, int32_t, int32_t, int32_t) {
+          return aux + (i64)in == (i64)out;
         });
   }
   if (order <= 12u) {
@@ -1122,6 +1150,7 @@ __device__ __forceinline__ bool restore_block(int32_t* x, uint32_t n, uint32_t t
 
 struct DecCfg {
   uint32_t channels, stereo_mode, bit_depth, n_blocks;
+  uint32_t lpc_fp64;  // LPC restore chain on the FP64 pipe (restore_block)
 };
 
 // K12a: one warp per frame-block, lane 0 parses.  blk_fs[b] = first sample of block b,
@@ -1255,12 +1284,16 @@ __global__ void __launch_bounds__(1024) k_restore_order(DecCfg cfg, const ChanHd
     if (key) order[atomicAdd(&cur[key], 1u)] = j;
   }
 }
-__global__ void __launch_bounds__(64) k_restore_blocks(DecCfg cfg, const u64* __restrict__ blk_fs,
+#ifndef LACB_RESTORE_TPB
+#define LACB_RESTORE_TPB 64
+#endif
+constexpr uint32_t kRestoreTpb = LACB_RESTORE_TPB;  // threads (channel-blocks) per restore CTA
+__global__ void __launch_bounds__(LACB_RESTORE_TPB) k_restore_blocks(DecCfg cfg, const u64* __restrict__ blk_fs,
                                                        const uint32_t* __restrict__ blk_size, int32_t* L, int32_t* R,
                                                        const ChanHdr* __restrict__ hdrs, uint32_t* blk_err,
                                                        const uint32_t* __restrict__ order,
                                                        const uint32_t* __restrict__ n_order) {
-  __shared__ int4 stage[2 * kRestoreDepth][64];
+  __shared__ int4 stage[2 * kRestoreDepth][kRestoreTpb];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *n_order) return;
   const uint32_t j = order[i];
@@ -1268,7 +1301,7 @@ __global__ void __launch_bounds__(64) k_restore_blocks(DecCfg cfg, const u64* __
   const uint32_t b = j / cfg.channels, ch = j - b * cfg.channels;
   const ChanHdr* h = hdrs + (size_t)b * 2u + ch;
   int32_t* x = (ch ? R : L) + blk_fs[b];
-  if (!restore_block(x, blk_size[b], h->type, h->order, h->coef, &stage[0][threadIdx.x], 64u))
+  if (!restore_block(x, blk_size[b], h->type, h->order, h->coef, &stage[0][threadIdx.x], kRestoreTpb, cfg.lpc_fp64 != 0u))
     atomicOr(&blk_err[b], 0x100u << ch);
 }
 // Folds the restore verdicts (bits 8/9) into the per-block code in the reference's order:

@@ -3,7 +3,8 @@ import sys, time
 sys.path.insert(0, "tests")
 import numpy as np, helpers as H
 secs = int(sys.argv[1]) if len(sys.argv) > 1 else 600
-cd = H.gpu_codec()
+import os
+cd = H.lacb_module().Codec(0, os.environ["LACB_LIB"]) if os.environ.get("LACB_LIB") else H.gpu_codec()  # LACB_LIB: an experimental build
 l, r, pk = H.synth(2, 96000 * secs, 24, want_packed=True)
 frames = 96000 * secs; nb = (frames + 16383) // 16384
 sizes = np.full(nb, 16384, dtype=np.uint32); sizes[-1] = frames - 16384 * (nb - 1)
