@@ -101,8 +101,16 @@ struct ASmem {
   static constexpr size_t oPthr = oU + (size_t)CAP * 4;
   static constexpr size_t oCpre = oPthr + (((size_t)(NT + 1) * 8 + 15) & ~(size_t)15);
   static constexpr size_t oFlg = oCpre + (size_t)(NT + 1) * 32;
-  static constexpr size_t oKpub = oFlg + (size_t)NT * 4;
-  static constexpr size_t oScr = oKpub + (size_t)NT * E;
+  // The K plane (one byte per sample) shares the Cpre area in full-size layouts, behind FbAll: the plane-count prefix
+  // exists only from the winner's prepare() to the segment tables (one barrier later it is dead), the K plane is
+  // written by the candidate passes before that and by the per-level / final passes after it.  The 16 KB this saves
+  // bring the layout from 215.6 to 199.2 KB, under the 196 KB carve-out: the SM keeps 32 KB of L1 instead of none, and
+  // the kernel's register spills (which otherwise go to L2) hit it.
+  static constexpr bool kAliasK = NT >= 64;
+  static constexpr size_t oKalias = oCpre + ((3 * (size_t)(MAXSEG + 1) * 8 + 15) & ~(size_t)15);
+  static_assert(!kAliasK || oKalias + (size_t)NT * E <= oFlg, "K plane must fit inside Cpre behind FbAll");
+  static constexpr size_t oKpub = kAliasK ? oKalias : oFlg + (size_t)NT * 4;
+  static constexpr size_t oScr = oFlg + (size_t)NT * 4 + (kAliasK ? 0 : (size_t)NT * E);
   static constexpr size_t oSegP = oScr + 64 * 8;
   static constexpr size_t oSegStat = oSegP + (MAXSEG + 1) * 8;
   static constexpr size_t oSelBits = oSegStat + (MAXSEG + 1) * 8;
