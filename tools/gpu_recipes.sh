@@ -38,6 +38,18 @@ for recipe in "$@"; do
       python tools/run_configs.py > $OUT/${TAG}_all_configs.jsonl 2> $OUT/${TAG}_all_configs.err; echo "configs rc=$?"; cat $OUT/${TAG}_all_configs.jsonl ;;
     cli)          # lac_cli wall times beside the reference CLI
       python tools/cli_timing.py > $OUT/${TAG}_cli_timing.jsonl 2> $OUT/${TAG}_cli_timing.err; echo "cli rc=$?"; cat $OUT/${TAG}_cli_timing.jsonl ;;
+    configs-host) # the BASELINE configs through the host-buffer C ABI (page-locked caller buffers)
+      CUDA_DEVICE_MAX_CONNECTIONS=32 python tools/run_configs_host.py > $OUT/${TAG}_all_configs_host.jsonl 2> $OUT/${TAG}_all_configs_host.err; echo "configs-host rc=$?"; cat $OUT/${TAG}_all_configs_host.jsonl ;;
+    trace)        # device timeline of every slice of one host encode + decode of the bench workload
+      CUDA_DEVICE_MAX_CONNECTIONS=32 LACB_TRACE=1 python tools/e2e_trace.py > $OUT/${TAG}_e2e_trace.txt 2>&1; echo "trace rc=$?"; grep "slice .*:\|slice .* done\|^it" $OUT/${TAG}_e2e_trace.txt | tail -24 ;;
+    ncu-probe)    # the stereo-probe analysis kernel (first k_analyze launch of an auto-stereo encode); LACB_PROBE_GANG=1 gives the one-warp-CTA form
+      ncu --set full --import-source on --clock-control none -k regex:k_analyze -c 1 -f -o $OUT/${TAG}_probe \
+          python tools/run_configs.py --only "24/192k" > $OUT/${TAG}_ncu_probe.log 2>&1; echo "ncu-probe rc=$?"
+      ncu -i $OUT/${TAG}_probe.ncu-rep --page raw --csv > $OUT/${TAG}_probe_raw.csv ;;
+    ncu-others)   # one full-size launch each of the parser, the emitter, the restore and the autocorrelation kernels
+      ncu --set full --clock-control none -k regex:"k_parse_blocks|k_emit|k_restore_blocks|k_autocorr_stream" -c 4 -f -o $OUT/${TAG}_others \
+          python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/${TAG}_ncu_others.log 2>&1; echo "ncu-others rc=$?"
+      ncu -i $OUT/${TAG}_others.ncu-rep --page raw --csv > $OUT/${TAG}_others_raw.csv ;;
     phase)        # clock64 phase counters of k_analyze (-DLACB_PHASE_CLK build made by `make -C lossless-audio-codec_b200 phase`)
       python tools/phase_clk.py lossless-audio-codec_b200/build/liblac_b200_phase.so > $OUT/${TAG}_phase_clocks.txt 2>&1; echo "phase rc=$?"; cat $OUT/${TAG}_phase_clocks.txt ;;
     *) echo "unknown recipe $recipe"; exit 2 ;;
