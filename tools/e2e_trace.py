@@ -8,8 +8,11 @@ cd = H.lacb_module().Codec(0, os.environ["LACB_LIB"]) if os.environ.get("LACB_LI
 l, r, pk = H.synth(2, 96000 * secs, 24, want_packed=True)
 frames = 96000 * secs; nb = (frames + 16383) // 16384
 sizes = np.full(nb, 16384, dtype=np.uint32); sizes[-1] = frames - 16384 * (nb - 1)
-h_in = cd.pinned(pk.size); h_in[:] = pk
-h_pay = cd.pinned(pk.size + (pk.size >> 2) + 4096); h_out = cd.pinned(pk.size)
+if os.environ.get("PAGEABLE"):  # what a one-shot lac_cli hands over: plain (mapped) memory, first call included
+    h_in = pk.copy(); h_pay = np.zeros(pk.size + (pk.size >> 2) + 4096, dtype=np.uint8); h_out = np.zeros(pk.size, dtype=np.uint8)
+else:
+    h_in = cd.pinned(pk.size); h_in[:] = pk
+    h_pay = cd.pinned(pk.size + (pk.size >> 2) + 4096); h_out = cd.pinned(pk.size)
 bb = np.zeros(nb, dtype=np.uint32)
 for it in range(3):
     t0 = time.perf_counter(); n = cd.encode_into(h_in, h_pay, bb, 24, 2, 1); t1 = time.perf_counter()
