@@ -670,8 +670,14 @@ static int encode_host_sliced(lacb_ctx* ctx, const lacb_enc_params* prm, int lay
   // Round 2, later: FOUR contexts, and the input of slice i + 2 is queued before the host waits for the sizes of slice
   // i -- with a look-ahead of one slice the copy of slice i + 1 only started when the sizes of slice i - 1 were known,
   // i.e. when its own analysis could already have begun (1.1 ms of idle SMs in front of the third slice).
-  static const uint32_t NK = getenv("LACB_ENC_KIDS") ? (uint32_t)atoi(getenv("LACB_ENC_KIDS")) : 4u;  // tuning knob
-  static const uint32_t AHEAD = getenv("LACB_ENC_AHEAD") ? (uint32_t)atoi(getenv("LACB_ENC_AHEAD")) : 2u;
+  static const uint32_t NK = [] {  // tuning knob, 2..8 contexts
+    const int v = getenv("LACB_ENC_KIDS") ? atoi(getenv("LACB_ENC_KIDS")) : 4;
+    return (uint32_t)(v < 2 ? 2 : (v > 8 ? 8 : v));
+  }();
+  static const uint32_t AHEAD = [] {  // tuning knob, slices queued ahead (capped by the contexts below)
+    const int v = getenv("LACB_ENC_AHEAD") ? atoi(getenv("LACB_ENC_AHEAD")) : 2;
+    return (uint32_t)(v < 1 ? 1 : (v > 7 ? 7 : v));
+  }();
   const uint32_t nkenc = ctx->max_streams >= 2u ? lacb_umin(NK, ctx->max_streams) : NK;  // the caller's cap on slices in flight
   const uint32_t ahead = lacb_umin(AHEAD ? AHEAD : 1u, nkenc - 1u);  // slices queued beyond the one being collected
   CKR(ensure_kids(ctx, nkenc));
