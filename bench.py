@@ -532,11 +532,18 @@ def main():
         pay_off += cap
     sizes_out = [0] * nctx
 
+    e2e_split = [0.0, 0.0]  # wall seconds inside the encode / decode calls of context 0 (timed steps only)
+
     def work(i):
         b0, b1, p0, p1, po, cap = parts[i]
         c = cds[i]
+        t_a = time.perf_counter()
         n = c.encode_into(h_in[p0:p1], h_payload[po:po + cap], h_bb[b0:b1], DEPTH, CHANNELS, STEREO_MODE)
+        t_b = time.perf_counter()
         c.decode_into(h_payload[po:po + n], sizes[b0:b1], h_bb[b0:b1], DEPTH, CHANNELS, STEREO_MODE, h_out[p0:p1])
+        if i == 0:
+            e2e_split[0] += t_b - t_a
+            e2e_split[1] += time.perf_counter() - t_b
         sizes_out[i] = n
 
     def step_host():
@@ -555,6 +562,7 @@ def main():
         lac_e2e = step_host()
         assert np.array_equal(h_out, pk), "host round trip does not restore the PCM"
     barrier()
+    e2e_split[0] = e2e_split[1] = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         lac_e2e = step_host()
@@ -640,6 +648,8 @@ def main():
             "e2e": None if not e2e_steps else {"value": pcm_bytes * world * e2e_steps / e2e_wall / 1e9, "unit": UNIT,
                     "h2d_bytes_per_step": pcm_bytes + lac_e2e, "d2h_bytes_per_step": lac_e2e + pcm_bytes,
                     "steps": e2e_steps, "contexts": nctx,
+                    "encode_ms_per_step": e2e_split[0] / e2e_steps * 1e3,  # rank 0's calls, wall clock
+                    "decode_ms_per_step": e2e_split[1] / e2e_steps * 1e3,
                     "copy_ceiling": pcm_bytes * world * e2e_steps / copy_wall / 1e9,
                     "frac_of_copy_ceiling": copy_wall / e2e_wall,
                     "copy_ceiling_note": "same pinned buffers and bytes per step (H2D PCM, D2H payload, H2D payload, D2H PCM), "
