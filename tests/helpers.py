@@ -308,6 +308,13 @@ def block_corpus():
     c["fullscale_toggle_2048"] = sat
     big = rng.integers(-(1 << 31), (1 << 31) - 1, 512).astype(np.int32)
     c["int32_noise_512"] = big
+    # strongly predictable material near the int32 limits: LPC wins with samples of ~2^29 / 2^30, so the decoder's
+    # LPC restore chain (FP64 form: sums of twelve 2^15 x 2^31 products) is exercised where exactness is tightest
+    for name, shift in (("ar4_2p29_4096", 16), ("ar4_2p30_2048", 17)):
+        nn = int(name.split("_")[-1])
+        big_ar = c["ar4_16384"][:nn].astype(np.int64) << shift
+        big_ar += rng.integers(-(1 << 20), 1 << 20, nn)
+        c[name] = np.clip(big_ar, -(1 << 31), (1 << 31) - 1).astype(np.int32)
     return c
 
 
@@ -382,3 +389,50 @@ def emu_codec():
             subprocess.check_call(["make", "-s", "-C", str(PKG_DIR), "emu"])
         _emu_codec = lacb_module().Codec(0, EMU_SO)
     return _emu_codec
+
+
+def craft_lpc_block(res, coefs, k=28) -> bytes:
+    """A hand-built block stream: LPC predictor with the given Q15 coefficients, unpartitioned, static Rice (mode 3)
+    with parameter k, residuals `res` (block/encoder.cpp:773-822 layout: type, order, coefficients, control byte,
+    (mode:2, k:5), tokens, zero padding).  The reference's encoder never produces LPC blocks with samples near the int32
+    limits (its autocorrelation wraps and the candidate is dropped), but its decoder accepts them."""
+    bits = []
+
+    def put(v, n):
+        for i in range(n - 1, -1, -1):
+            bits.append((v >> i) & 1)
+
+    put(2, 8)
+    put(len(coefs), 8)
+    for c in coefs:
+        put(int(c) & 0xFFFF, 16)
+    put((3 & 3) << 5, 8)   # control byte: base mode 3 (static Rice), not partitioned
+    put((3 << 5) | k, 7)   # the one partition: mode 3, k
+    for r in res:
+        r = int(r)
+        u = (r << 1) if r >= 0 else (((-r - 1) << 1) | 1)
+        q = u >> k
+        if q:
+            put((1 << q) - 1, q)
+        put(0, 1)
+        put(u & ((1 << k) - 1), k)
+    while len(bits) % 8:
+        bits.append(0)
+    return bytes(int("".join(map(str, bits[i:i + 8])), 2) for i in range(0, len(bits), 8))
+
+
+def lpc_fullscale_streams(count, seed=21):
+    """(stream, n) pairs: crafted LPC blocks of order 4..12 whose reconstruction runs up to (and sometimes beyond) the
+    int32 limits -- impulses of 2^27 .. 2^30 into slowly decaying predictors."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for it in range(count):
+        order = int(rng.choice([4, 6, 8, 10, 12]))
+        n = int(rng.choice([96, 512, 1000]))
+        # a stable-looking predictor: a dominant first tap below 1 and small higher taps
+        coefs = [int(rng.integers(20000, 32000))] + [int(rng.integers(-9000, 9000)) for _ in range(order - 1)]
+        res = rng.integers(-(1 << 16), 1 << 16, n)
+        for _ in range(int(rng.integers(1, 6))):
+            res[int(rng.integers(0, n))] = int(rng.choice([-1, 1])) * (1 << int(rng.integers(27, 31)))
+        out.append((craft_lpc_block(res, coefs), n))
+    return out

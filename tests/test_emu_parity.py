@@ -101,6 +101,12 @@ def test_restore_overflow_verdicts(cd):
     assert restore_overflow_fuzz(cd, 8, 10) > 40
 
 
+def test_lpc_restore_at_int32_limits(cd):
+    from test_gpu_parity import lpc_fullscale_check
+    accepted, rejected, peak = lpc_fullscale_check(cd, 120)
+    assert accepted > 20 and rejected > 20 and peak > (1 << 30)
+
+
 def test_sliced_host_pipeline():
     from test_gpu_parity import run_sliced
     run_sliced("emu_codec", 3)

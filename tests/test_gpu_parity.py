@@ -357,6 +357,29 @@ def test_restore_overflow_verdicts(cd):
     assert restore_overflow_fuzz(cd, 24, 25) > 300
 
 
+def lpc_fullscale_check(cd, count):
+    """LPC restore at the int32 limits (the FP64 form of the chain must be exact there): verdicts and samples equal to
+    the oracle decoder's on hand-built streams (helpers.craft_lpc_block)."""
+    accepted = rejected = 0
+    peak = 0
+    for stream, n in H.lpc_fullscale_streams(count):
+        ok_a, dec_a, bits_a = H.oracle().block_decode(stream, n)
+        ok_b, dec_b, bits_b = cd.block_decode(stream, n)
+        assert ok_a == ok_b
+        if ok_a:
+            assert bits_a == bits_b and np.array_equal(dec_a, dec_b)
+            accepted += 1
+            peak = max(peak, int(np.abs(dec_a.astype(np.int64)).max()))
+        else:
+            rejected += 1
+    return accepted, rejected, peak
+
+
+def test_lpc_restore_at_int32_limits(cd):
+    accepted, rejected, peak = lpc_fullscale_check(cd, 300)
+    assert accepted > 50 and rejected > 50 and peak > (1 << 30)
+
+
 def _shift_bits(data: bytes, k: int) -> bytes:
     """`data` behind k junk bits (ones), MSB first, zero padded to a byte"""
     v = (((1 << k) - 1) << (8 * len(data))) | int.from_bytes(data, "big")
